@@ -1,0 +1,283 @@
+// K2+K3: global stiffness assembly straight to CSR (replaces src/fea_solver.py:74-106).
+//
+// The reference emits 36 COO triplets per element and lets scipy sort / merge them.  Every
+// triplet of an element lives in one of four 3x3 node blocks, and the two diagonal blocks
+// exist for any node with an incident active element, so the CSR *structure* is fixed by
+// the directed node pairs (n1->n2, n2->n1) alone.  Pipeline (all on the caller's stream):
+//
+//   symbolic  count owned directed pairs per element -> exclusive scan -> emit
+//             (key = src_local<<dst_bits | dst, value = element id; per-node degree by integer
+//             atomics) -> stable LSD radix sort (radix_sort.cu) -> per node: unique
+//             neighbours (+1 for the diagonal block) -> exclusive scan -> row_ptr.
+//   numeric   one thread per owned node walks its sorted pair segment, evaluates S_e in
+//             registers (ke.cuh -- the COO stream and K_e are never materialised), sums
+//             duplicates in element order and the diagonal in (neighbour, element) order
+//             (fixed order => deterministic, "segmented scatter-add" without atomics), and
+//             writes the node's three CSR rows: col_idx ascending, explicit zeros kept.
+//
+// An element with n1 == n2 contributes S - S - S + S = 0 to its node's diagonal block: it
+// only makes the block exist, exactly as in the reference.
+#include "common.cuh"
+#include "ke.cuh"
+
+namespace {
+
+constexpr int AS_THREADS = 256;
+
+__device__ __forceinline__ bool owned(int32_t node, int64_t nb, int64_t ne) {
+  return node >= nb && node < ne;
+}
+
+__global__ void __launch_bounds__(AS_THREADS)
+edge_count_kernel(const int32_t* __restrict__ n1, const int32_t* __restrict__ n2,
+                  const uint8_t* __restrict__ active, int64_t n_elem, int64_t n_nodes, int64_t nb,
+                  int64_t ne, int32_t* __restrict__ cnt, int* __restrict__ bad_flag) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int c = 0;
+    if (!active || active[e]) {
+      const int32_t a = n1[e], b = n2[e];
+      if (a < 0 || b < 0 || a >= n_nodes || b >= n_nodes) {
+        *bad_flag = 1;
+      } else if (a == b) {
+        c = owned(a, nb, ne) ? 1 : 0;
+      } else {
+        c = (owned(a, nb, ne) ? 1 : 0) + (owned(b, nb, ne) ? 1 : 0);
+      }
+    }
+    cnt[e] = c;
+  }
+}
+
+__global__ void __launch_bounds__(AS_THREADS)
+edge_emit_kernel(const int32_t* __restrict__ n1, const int32_t* __restrict__ n2,
+                 const uint8_t* __restrict__ active, int64_t n_elem, int64_t nb, int64_t ne,
+                 int dst_bits, const int32_t* __restrict__ offs, uint64_t* __restrict__ keys,
+                 uint32_t* __restrict__ vals, int32_t* __restrict__ deg) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    if (active && !active[e]) continue;
+    const int32_t a = n1[e], b = n2[e];
+    int64_t o = offs[e];
+    if (owned(a, nb, ne)) {
+      keys[o] = ((uint64_t)(a - nb) << dst_bits) | (uint64_t)b;
+      vals[o] = (uint32_t)e;
+      atomicAdd(&deg[a - nb], 1);
+      ++o;
+    }
+    if (b != a && owned(b, nb, ne)) {
+      keys[o] = ((uint64_t)(b - nb) << dst_bits) | (uint64_t)a;
+      vals[o] = (uint32_t)e;
+      atomicAdd(&deg[b - nb], 1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AS_THREADS)
+block_count_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ edge_start,
+                   int64_t n_local, int64_t nb, int dst_bits, int32_t* __restrict__ bc) {
+  const uint64_t dmask = ((uint64_t)1 << dst_bits) - 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t es = edge_start[i], ee = edge_start[i + 1];
+    int c = 0;
+    if (ee > es) {
+      c = 1;  // diagonal block
+      const int64_t self = nb + i;
+      int64_t prev = -1;
+      for (int32_t k = es; k < ee; ++k) {
+        const int64_t dst = (int64_t)(keys[k] & dmask);
+        if (dst != prev && dst != self) ++c;
+        prev = dst;
+      }
+    }
+    bc[i] = c;
+  }
+}
+
+__global__ void __launch_bounds__(AS_THREADS)
+row_ptr_kernel(const int32_t* __restrict__ block_start, int64_t n_local, int32_t* __restrict__ row_ptr) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_local;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t bs = block_start[i];
+    if (i == n_local) {
+      row_ptr[3 * i] = 9 * bs;
+    } else {
+      const int32_t w = 3 * (block_start[i + 1] - bs);
+      row_ptr[3 * i] = 9 * bs;
+      row_ptr[3 * i + 1] = 9 * bs + w;
+      row_ptr[3 * i + 2] = 9 * bs + 2 * w;
+    }
+  }
+}
+
+__device__ __forceinline__ void write_block(int32_t* __restrict__ col_idx, double* __restrict__ val,
+                                            int64_t row0, int32_t w, int b, int64_t col_node,
+                                            const Sym3& s, double sign) {
+  const double m[3][3] = {{s.xx, s.xy, s.xz}, {s.xy, s.yy, s.yz}, {s.xz, s.yz, s.zz}};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int64_t p = row0 + (int64_t)a * w + 3 * b;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      col_idx[p + c] = (int32_t)(3 * col_node + c);
+      val[p + c] = sign * m[a][c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AS_THREADS)
+fill_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ evals,
+            const int32_t* __restrict__ edge_start, const int32_t* __restrict__ block_start,
+            int64_t n_local, int64_t nb, int dst_bits, const double* __restrict__ coords,
+            const int32_t* __restrict__ n1, const int32_t* __restrict__ n2, double E, double A,
+            double I, int32_t* __restrict__ col_idx, double* __restrict__ val) {
+  const uint64_t dmask = ((uint64_t)1 << dst_bits) - 1;
+  const BarConsts bc = myc_bar_consts(E, A, I);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t es = edge_start[i], ee = edge_start[i + 1];
+    if (ee == es) continue;
+    const int32_t bs = block_start[i];
+    const int32_t w = 3 * (block_start[i + 1] - bs);     // entries per row
+    const int64_t row0 = 9 * (int64_t)bs;
+    const int64_t self = nb + i;
+    Sym3 diag = {0, 0, 0, 0, 0, 0};
+    int b = 0, diag_pos = -1;
+    int32_t k = es;
+    while (k < ee) {
+      const int64_t dst = (int64_t)(keys[k] & dmask);
+      if (dst == self) { ++k; continue; }                // n1 == n2: contributes exact zeros
+      if (diag_pos < 0 && dst > self) diag_pos = b++;
+      Sym3 acc = {0, 0, 0, 0, 0, 0};
+      do {
+        const uint32_t e = evals[k];
+        const int64_t a = n1[e], c = n2[e];
+        double L;
+        const Sym3 s = myc_bar_block(coords[3 * a], coords[3 * a + 1], coords[3 * a + 2],
+                                     coords[3 * c], coords[3 * c + 1], coords[3 * c + 2], bc, &L);
+        acc.xx += s.xx; acc.xy += s.xy; acc.xz += s.xz; acc.yy += s.yy; acc.yz += s.yz; acc.zz += s.zz;
+        diag.xx += s.xx; diag.xy += s.xy; diag.xz += s.xz; diag.yy += s.yy; diag.yz += s.yz; diag.zz += s.zz;
+        ++k;
+      } while (k < ee && (int64_t)(keys[k] & dmask) == dst);
+      write_block(col_idx, val, row0, w, b, dst, acc, -1.0);
+      ++b;
+    }
+    if (diag_pos < 0) diag_pos = b;
+    write_block(col_idx, val, row0, w, diag_pos, self, diag, 1.0);
+  }
+}
+
+int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
+  int b = 1;
+  while (((int64_t)1 << b) < n) ++b;
+  return b;
+}
+
+}  // namespace
+
+extern "C" int myc_assemble_symbolic(myc_ctx* ctx, const int32_t* d_n1, const int32_t* d_n2,
+                                     const uint8_t* d_active, int64_t n_elem, int64_t n_nodes,
+                                     int64_t node_begin, int64_t node_end, int32_t* d_out_row_ptr,
+                                     int64_t* h_out_nnz, void* stream) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  ctx->plan_valid = false;
+  if (n_elem < 0 || n_nodes < 0 || node_begin < 0 || node_end < node_begin || node_end > n_nodes ||
+      !d_out_row_ptr || !h_out_nnz || (n_elem > 0 && (!d_n1 || !d_n2)))
+    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "assemble_symbolic: bad argument");
+  if (n_nodes >= ((int64_t)1 << 31) / 3 || n_elem >= ((int64_t)1 << 31))
+    MYC_FAIL(ctx, MYC_ERR_CAPACITY, "assemble_symbolic: mesh exceeds int32 DOF / element indices");
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_local = node_end - node_begin;
+  int64_t* h_pin = (int64_t*)ctx->h_pinned;
+
+  MYC_TRY(myc_ensure(ctx, ctx->edge_cnt, (size_t)(n_elem + 1) * sizeof(int32_t)));
+  MYC_TRY(myc_ensure(ctx, ctx->node_deg, (size_t)(n_local + 1) * sizeof(int32_t)));
+  MYC_TRY(myc_ensure(ctx, ctx->node_bc, (size_t)(n_local + 1) * sizeof(int32_t)));
+  MYC_TRY(myc_ensure(ctx, ctx->misc, 256));
+  int32_t* cnt = (int32_t*)ctx->edge_cnt.p;
+  int32_t* deg = (int32_t*)ctx->node_deg.p;
+  int32_t* nbc = (int32_t*)ctx->node_bc.p;
+  int* bad_flag = (int*)ctx->misc.p;
+  int64_t* d_total = (int64_t*)((char*)ctx->misc.p + 64);
+
+  MYC_CUDA(ctx, cudaMemsetAsync(bad_flag, 0, 128, st));
+  MYC_CUDA(ctx, cudaMemsetAsync(deg, 0, (size_t)(n_local + 1) * sizeof(int32_t), st));
+  const int g_elem = grid_for(ctx, ceil_div64(n_elem, AS_THREADS), 8);
+  const int g_node = grid_for(ctx, ceil_div64(n_local + 1, AS_THREADS), 8);
+  if (n_elem > 0) {
+    edge_count_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, n_nodes,
+                                                     node_begin, node_end, cnt, bad_flag);
+    MYC_LAUNCHED(ctx);
+  }
+  MYC_TRY(myc_exclusive_scan_i32(ctx, cnt, cnt, n_elem, false, d_total, st));
+  MYC_CUDA(ctx, cudaMemcpyAsync(h_pin, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  MYC_CUDA(ctx, cudaMemcpyAsync(h_pin + 1, bad_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MYC_CUDA(ctx, cudaStreamSynchronize(st));
+  const int64_t n_edges = h_pin[0];
+  if (*(int*)(h_pin + 1)) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "assemble_symbolic: element end node outside [0, n_nodes)");
+  if (n_edges >= ((int64_t)1 << 31)) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "assemble_symbolic: too many directed pairs for one device");
+
+  const int dst_bits = bits_for(n_nodes);
+  const int key_bits = dst_bits + bits_for(n_local);
+  for (int k = 0; k < 2; ++k) {
+    MYC_TRY(myc_ensure(ctx, ctx->sort_keys[k], (size_t)(n_edges + 1) * sizeof(uint64_t)));
+    MYC_TRY(myc_ensure(ctx, ctx->sort_vals[k], (size_t)(n_edges + 1) * sizeof(uint32_t)));
+  }
+  int sorted = 0;
+  if (n_edges > 0) {
+    edge_emit_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, node_begin, node_end,
+                                                    dst_bits, cnt, (uint64_t*)ctx->sort_keys[0].p,
+                                                    (uint32_t*)ctx->sort_vals[0].p, deg);
+    MYC_LAUNCHED(ctx);
+    MYC_TRY(myc_radix_sort_pairs(ctx, n_edges, key_bits, &sorted, st));
+  }
+  // per-node segments of the sorted stream
+  MYC_TRY(myc_exclusive_scan_i32(ctx, deg, deg, n_local, true, nullptr, st));
+  if (n_local > 0) {
+    block_count_kernel<<<g_node, AS_THREADS, 0, st>>>((const uint64_t*)ctx->sort_keys[sorted].p, deg,
+                                                      n_local, node_begin, dst_bits, nbc);
+    MYC_LAUNCHED(ctx);
+  }
+  MYC_TRY(myc_exclusive_scan_i32(ctx, nbc, nbc, n_local, true, d_total, st));
+  row_ptr_kernel<<<g_node, AS_THREADS, 0, st>>>(nbc, n_local, d_out_row_ptr);
+  MYC_LAUNCHED(ctx);
+  MYC_CUDA(ctx, cudaMemcpyAsync(h_pin, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  MYC_CUDA(ctx, cudaStreamSynchronize(st));
+  const int64_t nnz = 9 * h_pin[0];
+  if (nnz >= ((int64_t)1 << 31)) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "assemble_symbolic: nnz %lld exceeds int32 row_ptr", (long long)nnz);
+  *h_out_nnz = nnz;
+  ctx->plan_valid = true;
+  ctx->plan_n_elem = n_elem;
+  ctx->plan_n_nodes = n_nodes;
+  ctx->plan_node_begin = node_begin;
+  ctx->plan_node_end = node_end;
+  ctx->plan_n_edges = n_edges;
+  ctx->plan_nnz = nnz;
+  ctx->plan_sorted_buf = sorted;
+  ctx->plan_dst_bits = dst_bits;
+  return MYC_OK;
+}
+
+extern "C" int myc_assemble_numeric(myc_ctx* ctx, const double* d_coords, const int32_t* d_n1,
+                                    const int32_t* d_n2, double E, double A, double I,
+                                    int64_t nnz_capacity, const int32_t* d_row_ptr,
+                                    int32_t* d_out_col_idx, double* d_out_val, void* stream) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  if (!ctx->plan_valid) MYC_FAIL(ctx, MYC_ERR_STATE, "assemble_numeric: call myc_assemble_symbolic first");
+  if (nnz_capacity < ctx->plan_nnz) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "assemble_numeric: capacity %lld < nnz %lld", (long long)nnz_capacity, (long long)ctx->plan_nnz);
+  if (ctx->plan_nnz == 0) return MYC_OK;
+  if (!d_coords || !d_n1 || !d_n2 || !d_out_col_idx || !d_out_val || !d_row_ptr)
+    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "assemble_numeric: null pointer");
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n_local = ctx->plan_node_end - ctx->plan_node_begin;
+  const int g_node = grid_for(ctx, ceil_div64(n_local, AS_THREADS), 8);
+  fill_kernel<<<g_node, AS_THREADS, 0, (cudaStream_t)stream>>>(
+      (const uint64_t*)ctx->sort_keys[ctx->plan_sorted_buf].p,
+      (const uint32_t*)ctx->sort_vals[ctx->plan_sorted_buf].p, (const int32_t*)ctx->node_deg.p,
+      (const int32_t*)ctx->node_bc.p, n_local, ctx->plan_node_begin, ctx->plan_dst_bits, d_coords,
+      d_n1, d_n2, E, A, I, d_out_col_idx, d_out_val);
+  MYC_LAUNCHED(ctx);
+  return MYC_OK;
+}

@@ -1,0 +1,124 @@
+// Shared internals of libmycelium_fea_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mycelium_fea.h"
+
+#define MYC_SM_COUNT_FALLBACK 148
+
+// Growable device scratch buffer owned by the context.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct NcclApi;  // dist.cu
+
+struct PeerRange {  // half-open DOF range [lo, hi) of a global-length vector
+  int64_t lo = 0, hi = 0;
+};
+
+struct myc_ctx {
+  int device = 0;
+  int sm_count = MYC_SM_COUNT_FALLBACK;
+  char err[512] = {0};
+  int64_t launches = 0;
+
+  // ---- scratch arenas (grown on demand, never shrunk)
+  DevBuf scan_tmp;              // block sums of the exclusive scan (all levels)
+  DevBuf sort_keys[2];          // radix sort ping-pong
+  DevBuf sort_vals[2];
+  DevBuf sort_table;            // per-tile digit histograms
+  DevBuf edge_cnt;              // per-element emitted-edge count / offsets
+  DevBuf node_deg;              // per-owned-node incident edge count -> edge_start
+  DevBuf node_bc;               // per-owned-node block count -> block_start
+  DevBuf partials;              // per-block partial sums of the fused dots
+  DevBuf scalars;               // PcgScalars + counters
+  DevBuf vec[6];                // PCG work vectors (r, p(global), Ap, ...)
+  DevBuf misc;                  // small temporaries (flags, gather-sum output ...)
+  DevBuf lc[14];                // device copies owned by myc_load_case_host
+  void* h_pinned = nullptr;     // 4 KB pinned staging for host scalars
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  // ---- assembly plan retained between symbolic and numeric
+  bool plan_valid = false;
+  int64_t plan_n_elem = 0, plan_n_nodes = 0, plan_node_begin = 0, plan_node_end = 0;
+  int64_t plan_n_edges = 0, plan_nnz = 0;
+  int plan_sorted_buf = 0;      // which ping-pong buffer holds the sorted edges
+  int plan_dst_bits = 0;
+
+  // ---- distributed state
+  NcclApi* nccl = nullptr;
+  void* comm = nullptr;         // ncclComm_t
+  int rank = 0, world = 1;
+  int64_t* node_offsets = nullptr;   // world+1
+  PeerRange* recv_from = nullptr;    // [world] DOF ranges this rank receives from peer q
+  PeerRange* send_to = nullptr;      // [world] DOF ranges this rank sends to peer q
+};
+
+#define MYC_FAIL(ctx, code, ...)                                   \
+  do {                                                             \
+    if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+    return (code);                                                 \
+  } while (0)
+
+#define MYC_CUDA(ctx, call)                                                                  \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      MYC_FAIL(ctx, MYC_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,               \
+               cudaGetErrorString(e__));                                                     \
+  } while (0)
+
+#define MYC_TRY(call)            \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__ != MYC_OK) return rc__; \
+  } while (0)
+
+// Check the launch that was just issued.
+#define MYC_LAUNCHED(ctx)                                                                     \
+  do {                                                                                        \
+    (ctx)->launches++;                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess)                                                                   \
+      MYC_FAIL(ctx, MYC_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,            \
+               cudaGetErrorString(e__));                                                      \
+  } while (0)
+
+static inline int myc_ensure(myc_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return MYC_OK;
+  if (b.p) MYC_CUDA(ctx, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  MYC_CUDA(ctx, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return MYC_OK;
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Grid for grid-stride kernels: whole waves of the SM count, never more than the work.
+static inline int grid_for(const myc_ctx* ctx, int64_t n_tiles, int blocks_per_sm) {
+  int64_t full = (int64_t)ctx->sm_count * blocks_per_sm;
+  if (n_tiles < 1) n_tiles = 1;
+  return (int)(n_tiles < full ? n_tiles : full);
+}
+
+// ---- internal cross-file entry points ----------------------------------------------------
+// scan.cu: exclusive prefix sum of int32 counts, in place allowed; total (64-bit) to *d_total
+// (device) if non-null.  n+1-th element (the total) is also written at d_out[n] when
+// write_total_at_end is set (CSR-style offsets), truncated to int32 (caller checks d_total).
+int myc_exclusive_scan_i32(myc_ctx* ctx, const int32_t* d_in, int32_t* d_out, int64_t n,
+                           bool write_total_at_end, int64_t* d_total, cudaStream_t st);
+// radix_sort.cu: stable LSD sort of (key64, val32) pairs on the low `key_bits` bits.
+// Returns the index (0/1) of the ping-pong buffer holding the result.
+int myc_radix_sort_pairs(myc_ctx* ctx, int64_t n, int key_bits, int* out_buf, cudaStream_t st);
+
+// spmv.cu
+int myc_launch_spmv(myc_ctx* ctx, int64_t n_rows, const int32_t* rp, const int32_t* ci,
+                    const double* v, const double* x, double* y, cudaStream_t st);

@@ -1,0 +1,281 @@
+// K4: Dirichlet elimination in the full index space (replaces src/fea_solver.py:113-125 and
+// plays the role of MatZeroRowsColumnsIS, src/fea_petsc.cpp:309), the reaction gather-sum
+// (src/fea_solver.py:263-264), the solution merge (:131-133) and the explicit K_ff extraction
+// used for structure parity (:118).
+#include "common.cuh"
+#include "spmv.cuh"
+
+namespace {
+
+constexpr int DI_THREADS = 256;
+
+__global__ void __launch_bounds__(DI_THREADS)
+scatter_known_kernel(const int64_t* __restrict__ dofs, const double* __restrict__ vals, int64_t n_known,
+                     int64_t n_cols_global, int64_t row_offset, int64_t n_rows, double* __restrict__ ubc,
+                     double* __restrict__ dinv, int* __restrict__ bad_flag) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_known;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t dof = dofs[k];
+    if (dof < 0 || dof >= n_cols_global) { *bad_flag = 1; continue; }
+    ubc[dof] = vals[k];
+    const int64_t loc = dof - row_offset;
+    if (loc >= 0 && loc < n_rows) dinv[loc] = 0.0;        // 0 marks a known row
+  }
+}
+
+__global__ void __launch_bounds__(DI_THREADS)
+fill_kernel(double* __restrict__ p, int64_t n, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// dinv[i] = 1/(K_ii + reg) on free rows (dinv still 1 from the fill), untouched (0) on known rows
+__global__ void __launch_bounds__(DI_THREADS)
+jacobi_kernel(int64_t n_rows, int64_t row_offset, const int32_t* __restrict__ rp,
+              const int32_t* __restrict__ ci, const double* __restrict__ v, double reg,
+              double* __restrict__ dinv) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (dinv[i] == 0.0) continue;
+    const int32_t want = (int32_t)(row_offset + i);
+    double d = 0.0;
+    for (int32_t j = rp[i]; j < rp[i + 1]; ++j)
+      if (ci[j] == want) d += v[j];
+    dinv[i] = 1.0 / (d + reg);
+  }
+}
+
+struct EpiRhs {   // b = -(K u_bc) on free rows, 0 on known rows
+  static constexpr int NACC = 0;
+  double* b;
+  const double* dinv;
+  __device__ __forceinline__ void row(int64_t r, double s, double (&)[1]) const {
+    b[r] = dinv[r] != 0.0 ? -s : 0.0;
+  }
+};
+
+__global__ void __launch_bounds__(DI_THREADS)
+merge_kernel(int64_t n_rows, int64_t row_offset, const double* __restrict__ x,
+             const double* __restrict__ dinv, const double* __restrict__ ubc, double* __restrict__ U) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows;
+       i += (int64_t)gridDim.x * blockDim.x)
+    U[row_offset + i] = dinv[i] != 0.0 ? x[i] : ubc[row_offset + i];
+}
+
+// single block, fixed order: thread t sums idx t, t+T, ... then the block tree
+__global__ void __launch_bounds__(SP_THREADS)
+gather_sum_kernel(const double* __restrict__ v, const int64_t* __restrict__ idx, int64_t n, double* out) {
+  __shared__ double s_warp[SP_THREADS / 32];
+  double s = 0.0;
+  for (int64_t k = threadIdx.x; k < n; k += SP_THREADS) s += v[idx[k]];
+  s = myc_block_reduce(s, s_warp);
+  if (threadIdx.x == 0) *out = s;
+}
+
+// ---- explicit reduced matrix -----------------------------------------------------------
+__global__ void __launch_bounds__(DI_THREADS)
+free_flag_kernel(int64_t n, const double* __restrict__ dinv, int32_t* __restrict__ flag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flag[i] = dinv[i] != 0.0 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(DI_THREADS)
+reduced_count_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_t* __restrict__ ci,
+                     const double* __restrict__ dinv, const int32_t* __restrict__ free_index,
+                     int32_t* __restrict__ cnt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (dinv[i] == 0.0) continue;
+    int c = 0;
+    for (int32_t j = rp[i]; j < rp[i + 1]; ++j) c += dinv[ci[j]] != 0.0 ? 1 : 0;
+    cnt[free_index[i]] = c;
+  }
+}
+
+__global__ void __launch_bounds__(DI_THREADS)
+reduced_fill_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_t* __restrict__ ci,
+                    const double* __restrict__ v, const double* __restrict__ dinv,
+                    const int32_t* __restrict__ free_index, const int32_t* __restrict__ rrp,
+                    int32_t* __restrict__ rci, double* __restrict__ rv) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (dinv[i] == 0.0) continue;
+    int32_t o = rrp[free_index[i]];
+    for (int32_t j = rp[i]; j < rp[i + 1]; ++j) {
+      const int32_t c = ci[j];
+      if (dinv[c] != 0.0) { rci[o] = free_index[c]; rv[o] = v[j]; ++o; }
+    }
+  }
+}
+
+// ---- 3x3 node-block inverse --------------------------------------------------------------
+__global__ void __launch_bounds__(DI_THREADS)
+block3_kernel(int64_t n_nodes_local, int64_t row_offset, const int32_t* __restrict__ rp,
+              const int32_t* __restrict__ ci, const double* __restrict__ v,
+              const double* __restrict__ dinv, double reg, double* __restrict__ binv) {
+  for (int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nd < n_nodes_local;
+       nd += (int64_t)gridDim.x * blockDim.x) {
+    double m[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    const int32_t c0 = (int32_t)(row_offset + 3 * nd);
+    for (int a = 0; a < 3; ++a) {
+      const int64_t i = 3 * nd + a;
+      for (int32_t j = rp[i]; j < rp[i + 1]; ++j) {
+        const int32_t c = ci[j] - c0;
+        if (c >= 0 && c < 3) m[a][c] += v[j];
+      }
+      m[a][a] += reg;
+    }
+    bool fr[3];
+    for (int a = 0; a < 3; ++a) fr[a] = dinv[3 * nd + a] != 0.0;
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c)
+        if (!fr[a] || !fr[c]) m[a][c] = (a == c) ? 1.0 : 0.0;   // known DOF: identity row/col
+    // symmetric 3x3 inverse by cofactors
+    const double c00 = m[1][1] * m[2][2] - m[1][2] * m[2][1];
+    const double c01 = m[1][2] * m[2][0] - m[1][0] * m[2][2];
+    const double c02 = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+    const double det = m[0][0] * c00 + m[0][1] * c01 + m[0][2] * c02;
+    const double id = 1.0 / det;
+    double inv[3][3];
+    inv[0][0] = c00 * id;
+    inv[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) * id;
+    inv[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) * id;
+    inv[1][0] = c01 * id;
+    inv[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) * id;
+    inv[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) * id;
+    inv[2][0] = c02 * id;
+    inv[2][1] = (m[0][1] * m[2][0] - m[0][0] * m[2][1]) * id;
+    inv[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) binv[9 * nd + 3 * a + c] = (fr[a] && fr[c]) ? inv[a][c] : 0.0;
+  }
+}
+
+}  // namespace
+
+extern "C" int myc_apply_dirichlet(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
+                                   const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
+                                   const int64_t* d_known_dofs, const double* d_known_vals, int64_t n_known,
+                                   double reg, double* d_out_ubc, double* d_out_rhs, double* d_out_dinv,
+                                   void* stream) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  if (n_rows < 0 || n_cols_global < n_rows || row_offset < 0 || row_offset + n_rows > n_cols_global ||
+      n_known < 0 || !d_row_ptr || (n_known > 0 && (!d_known_dofs || !d_known_vals)) ||
+      (n_cols_global > 0 && !d_out_ubc) || (n_rows > 0 && (!d_out_rhs || !d_out_dinv)))
+    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "apply_dirichlet: bad argument");
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  MYC_TRY(myc_ensure(ctx, ctx->misc, 256));
+  int* bad_flag = (int*)ctx->misc.p;
+  MYC_CUDA(ctx, cudaMemsetAsync(bad_flag, 0, sizeof(int), st));
+  MYC_CUDA(ctx, cudaMemsetAsync(d_out_ubc, 0, (size_t)n_cols_global * sizeof(double), st));
+  if (n_rows == 0) return MYC_OK;
+  const int g_rows = grid_for(ctx, ceil_div64(n_rows, DI_THREADS), 8);
+  fill_kernel<<<g_rows, DI_THREADS, 0, st>>>(d_out_dinv, n_rows, 1.0);
+  MYC_LAUNCHED(ctx);
+  if (n_known > 0) {
+    scatter_known_kernel<<<grid_for(ctx, ceil_div64(n_known, DI_THREADS), 8), DI_THREADS, 0, st>>>(
+        d_known_dofs, d_known_vals, n_known, n_cols_global, row_offset, n_rows, d_out_ubc, d_out_dinv, bad_flag);
+    MYC_LAUNCHED(ctx);
+  }
+  jacobi_kernel<<<g_rows, DI_THREADS, 0, st>>>(n_rows, row_offset, d_row_ptr, d_col_idx, d_val, reg, d_out_dinv);
+  MYC_LAUNCHED(ctx);
+  const int grid = grid_for(ctx, ceil_div64(n_rows, SP_ROWS), SP_BLOCKS_PER_SM);
+  EpiRhs epi{d_out_rhs, d_out_dinv};
+  myc_spmv_kernel<EpiRhs><<<grid, SP_THREADS, 0, st>>>(n_rows, d_row_ptr, d_col_idx, d_val, d_out_ubc, epi,
+                                                       nullptr, nullptr, nullptr, nullptr);
+  MYC_LAUNCHED(ctx);
+  int* h = (int*)ctx->h_pinned;
+  MYC_CUDA(ctx, cudaMemcpyAsync(h, bad_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MYC_CUDA(ctx, cudaStreamSynchronize(st));
+  if (*h) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "apply_dirichlet: known DOF outside [0, n_dof)");
+  return MYC_OK;
+}
+
+extern "C" int myc_block3_inverse(myc_ctx* ctx, int64_t n_rows, int64_t row_offset, const int32_t* d_row_ptr,
+                                  const int32_t* d_col_idx, const double* d_val, const double* d_dinv,
+                                  double reg, double* d_out_binv, void* stream) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  if (n_rows < 0 || n_rows % 3 || !d_row_ptr || (n_rows > 0 && (!d_dinv || !d_out_binv)))
+    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "block3_inverse: bad argument (n_rows must be a multiple of 3)");
+  if (n_rows == 0) return MYC_OK;
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  block3_kernel<<<grid_for(ctx, ceil_div64(n_rows / 3, DI_THREADS), 8), DI_THREADS, 0, (cudaStream_t)stream>>>(
+      n_rows / 3, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv, reg, d_out_binv);
+  MYC_LAUNCHED(ctx);
+  return MYC_OK;
+}
+
+extern "C" int myc_merge_solution(myc_ctx* ctx, int64_t n_rows, int64_t row_offset, const double* d_x,
+                                  const double* d_dinv, const double* d_ubc, double* d_out_U, void* stream) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  if (n_rows < 0 || (n_rows > 0 && (!d_x || !d_dinv || !d_ubc || !d_out_U)))
+    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "merge_solution: bad argument");
+  if (n_rows == 0) return MYC_OK;
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  merge_kernel<<<grid_for(ctx, ceil_div64(n_rows, DI_THREADS), 8), DI_THREADS, 0, (cudaStream_t)stream>>>(
+      n_rows, row_offset, d_x, d_dinv, d_ubc, d_out_U);
+  MYC_LAUNCHED(ctx);
+  return MYC_OK;
+}
+
+extern "C" int myc_gather_sum(myc_ctx* ctx, const double* d_v, const int64_t* d_idx, int64_t n,
+                              double* h_out_sum, void* stream) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  if (n < 0 || !h_out_sum || (n > 0 && (!d_v || !d_idx))) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "gather_sum: bad argument");
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  MYC_TRY(myc_ensure(ctx, ctx->misc, 256));
+  double* d_out = (double*)((char*)ctx->misc.p + 128);
+  gather_sum_kernel<<<1, SP_THREADS, 0, st>>>(d_v, d_idx, n, d_out);
+  MYC_LAUNCHED(ctx);
+  double* h = (double*)ctx->h_pinned;
+  MYC_CUDA(ctx, cudaMemcpyAsync(h, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+  MYC_CUDA(ctx, cudaStreamSynchronize(st));
+  *h_out_sum = *h;
+  return MYC_OK;
+}
+
+extern "C" int myc_reduce_csr(myc_ctx* ctx, int64_t n_rows, const int32_t* d_row_ptr, const int32_t* d_col_idx,
+                              const double* d_val, const double* d_dinv, int32_t* d_out_free_index,
+                              int32_t* d_out_row_ptr, int32_t* d_out_col_idx, double* d_out_val,
+                              int64_t* h_out_n_free, int64_t* h_out_nnz, void* stream) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  if (n_rows < 0 || !d_row_ptr || !d_out_free_index || !d_out_row_ptr || !h_out_n_free || !h_out_nnz ||
+      (n_rows > 0 && !d_dinv))
+    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "reduce_csr: bad argument");
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  MYC_TRY(myc_ensure(ctx, ctx->misc, 256));
+  int64_t* d_tot = (int64_t*)((char*)ctx->misc.p + 64);
+  int64_t* h = (int64_t*)ctx->h_pinned;
+  const int g = grid_for(ctx, ceil_div64(n_rows, DI_THREADS), 8);
+  // free_index = exclusive scan of the free flags (the compacted numbering of np.setdiff1d)
+  if (n_rows > 0) {
+    free_flag_kernel<<<g, DI_THREADS, 0, st>>>(n_rows, d_dinv, d_out_free_index);
+    MYC_LAUNCHED(ctx);
+  }
+  MYC_TRY(myc_exclusive_scan_i32(ctx, d_out_free_index, d_out_free_index, n_rows, false, d_tot, st));
+  MYC_CUDA(ctx, cudaMemcpyAsync(h, d_tot, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  MYC_CUDA(ctx, cudaStreamSynchronize(st));
+  const int64_t n_free = h[0];
+  *h_out_n_free = n_free;
+  if (d_out_col_idx == nullptr) {   // phase 1: row_ptr + nnz
+    MYC_CUDA(ctx, cudaMemsetAsync(d_out_row_ptr, 0, (size_t)(n_free + 1) * sizeof(int32_t), st));
+    if (n_rows > 0) {
+      reduced_count_kernel<<<g, DI_THREADS, 0, st>>>(n_rows, d_row_ptr, d_col_idx, d_dinv, d_out_free_index, d_out_row_ptr);
+      MYC_LAUNCHED(ctx);
+    }
+    MYC_TRY(myc_exclusive_scan_i32(ctx, d_out_row_ptr, d_out_row_ptr, n_free, true, d_tot, st));
+    MYC_CUDA(ctx, cudaMemcpyAsync(h, d_tot, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaStreamSynchronize(st));
+    *h_out_nnz = h[0];
+    return MYC_OK;
+  }
+  if (!d_out_val) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "reduce_csr: d_out_val is null");
+  if (n_rows > 0) {
+    reduced_fill_kernel<<<g, DI_THREADS, 0, st>>>(n_rows, d_row_ptr, d_col_idx, d_val, d_dinv, d_out_free_index,
+                                                  d_out_row_ptr, d_out_col_idx, d_out_val);
+    MYC_LAUNCHED(ctx);
+  }
+  return MYC_OK;
+}

@@ -1,0 +1,303 @@
+"""Drop-in for the reference's ``src/fea_solver.py`` / ``src/fea_solver_no_plotting.py``.
+
+Same entry point (``fea_solver(results_dir, tol)``; CLI ``python -m
+mycelium_fea_project_b200.fea_solver <results_dir>``), same constants, same
+``results/sim_*`` input files and ``fea_results/`` output files, and the same three inner
+functions a caller can use one at a time:
+
+    bar_stiffness_bulk(p1s, p2s, E, A, I)            -> (K (N,6,6), L)       fea_solver.py:30
+    assemble_global_stiffness(coords, elems, active) -> scipy.sparse.csr_matrix        :74
+    solve_system(K, known_dofs, known_vals)          -> U                             :112
+
+All arithmetic runs in hand-written sm_100a CUDA kernels through the C-ABI
+(include/mycelium_fea.h); numpy / pandas / scipy appear only as the containers the reference's
+signatures use.  The linear solve is a Jacobi- (or 3x3 block-Jacobi-) preconditioned CG instead
+of SuperLU, run to ``PCG_RTOL`` (displacements agree with the reference's direct solve to 1e-8
+relative L2 -- tests/test_gpu_parity.py).  There is no CPU fallback.
+
+The module-level constants are read at call time and may be overridden, because the
+reference's committed goldens were produced with other values than the committed source
+(SURVEY.md section 0.4).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import device as dv
+from ._lib import MyceliumFeaError
+
+# ---------------------------------------------------------------------------------------------
+# Material & simulation parameters -- same expressions as src/fea_solver.py:14-28
+# ---------------------------------------------------------------------------------------------
+E_mod = 2500
+d = 0.0002
+t = 0.000001
+A = 3.14 * ((d / 2) ** 2 - (d / 2 - t) ** 2)
+I = A * 0.001
+N_STEPS = 40
+DISPLACEMENT_MAX = 0.02
+MAX_STRAIN = 0.018
+MAX_STRESS = E_mod * MAX_STRAIN
+GRIP_LENGTH = 1.5
+REGULARISATION = 1e-12          # fea_solver.py:125
+
+# solver knobs (not in the reference, which uses a direct solve)
+PCG_RTOL = 1e-10
+PCG_MAXIT = 2_000_000
+PCG_PRECOND = "jacobi"          # or "block3"
+
+
+def _ctx():
+    return dv.Context.get()
+
+
+def _dev(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(_ctx().device)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's three inner functions
+# ---------------------------------------------------------------------------------------------
+def bar_stiffness_bulk(p1s, p2s, E=None, A=None, I=None):
+    """K_e (N,6,6) and L (N,) of N two-node bars; replaces fea_solver.py:30-68."""
+    E = E_mod if E is None else E
+    A_ = globals()["A"] if A is None else A
+    I_ = globals()["I"] if I is None else I
+    p1 = _dev(np.asarray(p1s, dtype=np.float64).reshape(-1, 3), np.float64)
+    p2 = _dev(np.asarray(p2s, dtype=np.float64).reshape(-1, 3), np.float64)
+    if p1.shape != p2.shape:
+        raise ValueError("p1s and p2s must have the same shape")
+    K, L = dv.bar_stiffness(_ctx(), p1, p2, E, A_, I_)
+    return K.cpu().numpy(), L.cpu().numpy()
+
+
+def _elem_columns(elems):
+    """n1/n2 columns of the reference's elements DataFrame (or any mapping / (n1,n2) pair)."""
+    if isinstance(elems, (tuple, list)) and len(elems) == 2:
+        return np.asarray(elems[0]), np.asarray(elems[1])
+    n1 = elems["n1"]
+    n2 = elems["n2"]
+    return np.asarray(getattr(n1, "values", n1)), np.asarray(getattr(n2, "values", n2))
+
+
+def assemble_global_stiffness_device(coords, elems, active) -> dv.DeviceCSR:
+    n1, n2 = _elem_columns(elems)
+    mesh = dv.DeviceMesh.from_host(coords, n1, n2, active)
+    return dv.assemble(_ctx(), mesh, E_mod, globals()["A"], globals()["I"])
+
+
+def assemble_global_stiffness(coords, elems, active):
+    """Global K as scipy CSR (int32 indices, sorted columns, duplicates summed, explicit zeros
+    kept); replaces fea_solver.py:74-106."""
+    return assemble_global_stiffness_device(coords, elems, active).to_scipy()
+
+
+def solve_system(K, known_dofs, known_vals, return_info=False):
+    """U (n_dof,) with U[known] = known_vals; replaces fea_solver.py:112-135.
+
+    ``K`` may be a scipy sparse matrix (as the reference passes) or a DeviceCSR."""
+    ctx = _ctx()
+    Kd = K if isinstance(K, dv.DeviceCSR) else dv.DeviceCSR.from_scipy(K)
+    kd = np.asarray(known_dofs, dtype=np.int64)
+    if len(np.unique(kd)) != len(kd):
+        raise ValueError("known_dofs contains duplicates")
+    sysd = dv.apply_dirichlet(ctx, Kd, _dev(kd, np.int64), _dev(known_vals, np.float64), REGULARISATION,
+                              block3=(PCG_PRECOND == "block3"))
+    x, iters, relres = dv.pcg(ctx, Kd, sysd, precond=PCG_PRECOND, rtol=PCG_RTOL, maxit=PCG_MAXIT)
+    U = dv.merge_solution(ctx, Kd, sysd, x).cpu().numpy()
+    if return_info:
+        return U, {"iterations": iters, "relres": relres, "true_relres": dv.true_residual(ctx, Kd, sysd, x)}
+    return U
+
+
+# ---------------------------------------------------------------------------------------------
+# host logic of the step loop: grips and Dirichlet sets (fea_solver.py:205-210, 223-245)
+# ---------------------------------------------------------------------------------------------
+LOAD_CASES = {            # name -> (grip axis, prescribed component)
+    "Y": (1, 1),          # the reference's only case: y grips, stretch in y
+    "X": (0, 0),          # x grips, stretch in x
+    "shear": (1, 0),      # y grips, prescribed x displacement
+}
+
+
+def grip_nodes(coords, tol=None, axis=1):
+    """(hi, lo) node ids within ``tol`` of the max / min coordinate (fea_solver.py:205-210)."""
+    tol = GRIP_LENGTH if tol is None else tol
+    c = np.asarray(coords)[:, axis]
+    ids = np.arange(len(c))
+    return ids[np.abs(c - c.max()) < tol], ids[np.abs(c - c.min()) < tol]
+
+
+def build_bc(hi_nodes, lo_nodes, d_hi, d_lo, comp=1):
+    """known_dofs / known_vals with the reference's dict semantics (fea_solver.py:223-245):
+    hi grip inserted first, then lo; a node in both keeps its first position and takes the lo
+    value; the two non-prescribed components are clamped to 0."""
+    hi = np.asarray(hi_nodes, dtype=np.int64)
+    lo = np.asarray(lo_nodes, dtype=np.int64)
+    lo_new = lo[~np.isin(lo, hi)]
+    order = np.concatenate([hi, lo_new])
+    val = np.where(np.isin(order, lo), float(d_lo), float(d_hi))
+    known_dofs = (3 * order[:, None] + np.arange(3)).ravel()
+    known_vals = np.zeros((len(order), 3))
+    known_vals[:, comp] = val
+    return known_dofs, known_vals.ravel()
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident load case (what the step loop and bench.py run)
+# ---------------------------------------------------------------------------------------------
+class LoadCaseResult:
+    __slots__ = ("U", "total_force", "iterations", "relres", "K", "system", "x", "ms_assemble", "ms_solve")
+
+
+def analyze_load_case(mesh: dv.DeviceMesh, known_dofs, known_vals, react_dofs=None, x0=None,
+                      rtol=None, precond=None, K=None) -> LoadCaseResult:
+    """assemble -> Dirichlet -> PCG -> U (-> reactions), everything staying on the device.
+    ``known_dofs``/``known_vals``/``react_dofs`` may be numpy arrays or device tensors."""
+    ctx = _ctx()
+    rtol = PCG_RTOL if rtol is None else rtol
+    precond = PCG_PRECOND if precond is None else precond
+    as_dev = lambda a, dt: a if isinstance(a, torch.Tensor) else _dev(a, dt)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    if K is None:
+        K = dv.assemble(ctx, mesh, E_mod, globals()["A"], globals()["I"])
+    ev[1].record()
+    sysd = dv.apply_dirichlet(ctx, K, as_dev(known_dofs, np.int64), as_dev(known_vals, np.float64),
+                              REGULARISATION, block3=(precond == "block3"))
+    x, iters, relres = dv.pcg(ctx, K, sysd, x0=x0, precond=precond, rtol=rtol, maxit=PCG_MAXIT)
+    out = LoadCaseResult()
+    out.U = dv.merge_solution(ctx, K, sysd, x)
+    out.total_force = None
+    if react_dofs is not None:
+        F = dv.spmv(ctx, K, out.U)                                       # fea_solver.py:257
+        out.total_force = dv.gather_sum(ctx, F, as_dev(react_dofs, np.int64))   # :263-264
+    ev[2].record()
+    ev[2].synchronize()
+    out.iterations, out.relres, out.K, out.system, out.x = iters, relres, K, sysd, x
+    out.ms_assemble, out.ms_solve = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# the driver (fea_solver.py:186-335)
+# ---------------------------------------------------------------------------------------------
+def load_snapshot(results_dir):
+    """(coords, n1, n2) from nodes.csv / elements.csv (fea_solver.py:193-196); a ``mesh.npz``
+    side-car, if present, is preferred (CSV parsing dominates at >= 2048^2)."""
+    side = os.path.join(results_dir, "mesh.npz")
+    if os.path.isfile(side):
+        z = np.load(side)
+        return z["coords"], z["n1"], z["n2"]
+    import pandas as pd
+    nodes = pd.read_csv(os.path.join(results_dir, "nodes.csv"))
+    elems = pd.read_csv(os.path.join(results_dir, "elements.csv"))
+    return nodes[["x", "y", "z"]].values, elems["n1"].values, elems["n2"].values
+
+
+def fea_ramp(coords, n1, n2, tol=None, load_case="Y", warm_start=True, verbose=False):
+    """The displacement ramp on in-memory arrays; returns the per-step records
+    (stress, active, disp, force_disp) the reference accumulates (fea_solver.py:200-203)."""
+    ctx = _ctx()
+    tol = GRIP_LENGTH if tol is None else tol
+    axis, comp = LOAD_CASES[load_case]
+    coords = np.asarray(coords, dtype=np.float64)
+    mesh = dv.DeviceMesh.from_host(coords, n1, n2)
+    hi, lo = grip_nodes(coords, tol, axis)
+    react = _dev(3 * hi + comp, np.int64)
+    rec = {"stress": [], "active": [], "disp": [], "force_disp": [], "iterations": []}
+    x_prev, step_prev, topology_changed = None, 0, False
+    for step in range(N_STEPS):
+        f = step / (N_STEPS - 1)
+        d_hi, d_lo = +DISPLACEMENT_MAX * f, -DISPLACEMENT_MAX * f
+        if verbose:
+            print(f"Step {step + 1}/{N_STEPS} | d_hi={d_hi:.3f}, d_lo={d_lo:.3f}")
+        known_dofs, known_vals = build_bc(hi, lo, d_hi, d_lo, comp)
+        x0 = None
+        if warm_start and x_prev is not None and step_prev > 0 and not topology_changed:
+            # The response is linear in the load factor while no element fails, so the scaled
+            # previous solution is already converged.  After a failure we restart from 0: a
+            # warm start would leave stale displacements on pieces that have become detached
+            # (their only stiffness is the 1e-12 shift, invisible to the residual), whereas
+            # the reference's direct solve returns exactly 0 there.
+            x0 = x_prev * (step / step_prev)
+        try:
+            res = analyze_load_case(mesh, known_dofs, known_vals, react_dofs=react, x0=x0)
+        except MyceliumFeaError as exc:              # the reference's LinAlgError branch (:250-254)
+            print(f"Solver failure at step {step + 1}: {exc}. Saving partial results and stopping.")
+            break
+        x_prev, step_prev = res.x, step
+        rec["force_disp"].append([d_hi - d_lo, res.total_force])
+        n_before = int(mesh.active.sum().item())
+        stress, n_active = dv.strain_update(ctx, mesh, res.U, E_mod, MAX_STRAIN)     # :269-284
+        topology_changed = n_active != n_before
+        rec["stress"].append(stress.cpu().numpy())
+        rec["active"].append(mesh.active.cpu().numpy().astype(bool))
+        rec["disp"].append(res.U.cpu().numpy())
+        rec["iterations"].append(res.iterations)
+        if n_active == 0:
+            if verbose:
+                print(f"Simulation stopped early at step {step + 1}.")
+            break
+    return rec
+
+
+def write_results(fea_dir, rec, n_elems, total_time=None):
+    """The reference's four CSVs + runtime.txt (fea_solver.py:298-333), same columns."""
+    import pandas as pd
+    os.makedirs(fea_dir, exist_ok=True)
+    cols = [f"elem_{i}" for i in range(n_elems)]
+    steps = np.arange(1, len(rec["stress"]) + 1)
+    df = pd.DataFrame(rec["stress"], columns=cols)
+    df["step"] = steps
+    df.to_csv(os.path.join(fea_dir, "stress_record.csv"), index=False)
+    df = pd.DataFrame(rec["active"], columns=cols)
+    df["step"] = steps
+    df.to_csv(os.path.join(fea_dir, "active_elements.csv"), index=False)
+    n_dof = len(rec["disp"][0]) if rec["disp"] else 0
+    df = pd.DataFrame(rec["disp"], columns=np.arange(n_dof))
+    df["step"] = steps
+    df.to_csv(os.path.join(fea_dir, "node_displacements.csv"), index=False)
+    pd.DataFrame(rec["force_disp"], columns=["total_displacement", "total_force"]).to_csv(
+        os.path.join(fea_dir, "force_displacement.csv"), index=False)
+    if total_time is not None:
+        with open(os.path.join(fea_dir, "runtime.txt"), "w") as f:
+            f.write(f"Total FEA runtime: {total_time:.6f} seconds\n")
+
+
+def fea_solver(results_dir, tol=None, load_case="Y", binary_outputs=None):
+    """Run the 40-step ramp on ``results_dir`` and write ``fea_results/``; same contract as
+    the reference's fea_solver(results_dir, tol=GRIP_LENGTH) (fea_solver.py:186)."""
+    start = time.time()
+    print(f"Running FEA on geometry from {results_dir}")
+    fea_dir = os.path.join(results_dir, "fea_results")
+    os.makedirs(fea_dir, exist_ok=True)
+    coords, n1, n2 = load_snapshot(results_dir)
+    rec = fea_ramp(coords, n1, n2, tol=tol, load_case=load_case, verbose=True)
+    n_dof = 3 * len(coords)
+    if binary_outputs is None:
+        binary_outputs = n_dof > 2_000_000       # one CSV column per DOF is unusable beyond this
+    if binary_outputs:
+        np.savez_compressed(os.path.join(fea_dir, "records.npz"), stress=np.array(rec["stress"]),
+                            active=np.array(rec["active"]), disp=np.array(rec["disp"]),
+                            force_disp=np.array(rec["force_disp"]))
+    else:
+        write_results(fea_dir, rec, len(n1))
+    total = time.time() - start
+    with open(os.path.join(fea_dir, "runtime.txt"), "w") as f:
+        f.write(f"Total FEA runtime: {total:.6f} seconds\n")
+    print(f"FEA completed. Results saved to {fea_dir}")
+    print(f"Total runtime: {total:.3f} seconds")
+    return rec
+
+
+if __name__ == "__main__":
+    if len(sys.argv) < 2:
+        print("Usage: python fea_solver.py <results_dir>")
+        sys.exit()
+    fea_solver(sys.argv[1], tol=GRIP_LENGTH)
