@@ -59,6 +59,15 @@ const char* myc_last_error(const myc_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py "gpu_launches"). */
 int64_t myc_launch_count(const myc_ctx* ctx);
 
+/* Sampled device timing of the dominant kernel (the fused SpMV inside myc_pcg_solve), for the
+ * live roofline figure of bench.py.  reset(enable): clears the counters and switches sampling
+ * on/off (off by default; when on, every 32nd SpMV launch of a solve is bracketed by CUDA
+ * events on the solve's stream).  get: out[0] = summed duration of the sampled launches (ms),
+ * out[1] = number of sampled launches, out[2] = summed algorithmic bytes of the sampled
+ * launches (12*nnz + 20*n_rows each), out[3] = total SpMV launches since reset. */
+int myc_profile_reset(myc_ctx* ctx, int enable);
+int myc_profile_get(myc_ctx* ctx, double* h_out4);
+
 /* ------------------------------------------------------------------------------------------
  * K1  element stiffness.  Replaces bar_stiffness_bulk(p1s,p2s,E,A,I) -> (K(N,6,6), L(N,))
  *     src/fea_solver.py:30-68   (C++ twin: element_stiffness_6x6, src/fea_petsc.cpp:88-140)

@@ -58,6 +58,8 @@ SIGNATURES = {
     "myc_destroy": [_p],
     "myc_last_error": [_p],
     "myc_launch_count": [_p],
+    "myc_profile_reset": [_p, _int],
+    "myc_profile_get": [_p, _pf64],
     "myc_bar_stiffness_bulk": [_p, _p, _p, _i64, _f64, _f64, _f64, _p, _p, _p],
     "myc_assemble_symbolic": [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _pi64, _p],
     "myc_assemble_numeric": [_p, _p, _p, _p, _f64, _f64, _f64, _i64, _p, _p, _p, _p],

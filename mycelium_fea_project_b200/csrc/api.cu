@@ -25,6 +25,10 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
   }
   myc_ctx* ctx = new myc_ctx();
   ctx->device = device_ordinal;
+  {
+    const char* e = getenv("MYC_FORCE_PLAIN_SPMV");
+    ctx->force_plain_spmv = e && e[0] == '1';
+  }
   e = cudaSetDevice(device_ordinal);
   cudaDeviceProp prop;
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device_ordinal);
@@ -58,7 +62,29 @@ extern "C" int myc_destroy(myc_ctx* ctx) {
   for (DevBuf& b : ctx->lc) if (b.p) cudaFree(b.p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (cudaEvent_t e : ctx->prof_ev) if (e) cudaEventDestroy(e);
   delete ctx;
+  return MYC_OK;
+}
+
+extern "C" int myc_profile_reset(myc_ctx* ctx, int enable) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  ctx->prof_on = enable != 0;
+  ctx->prof_ms = ctx->prof_bytes = 0.0;
+  ctx->prof_samples = ctx->prof_launches = 0;
+  if (ctx->prof_on && !ctx->prof_ev[0]) {
+    MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < 2 * myc_ctx::PROF_PAIRS; ++i) MYC_CUDA(ctx, cudaEventCreate(&ctx->prof_ev[i]));
+  }
+  return MYC_OK;
+}
+
+extern "C" int myc_profile_get(myc_ctx* ctx, double* h_out4) {
+  if (!ctx || !h_out4) return MYC_ERR_BAD_ARG;
+  h_out4[0] = ctx->prof_ms;
+  h_out4[1] = (double)ctx->prof_samples;
+  h_out4[2] = ctx->prof_bytes;
+  h_out4[3] = (double)ctx->prof_launches;
   return MYC_OK;
 }
 

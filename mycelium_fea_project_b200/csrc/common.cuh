@@ -26,6 +26,7 @@ struct myc_ctx {
   int sm_count = MYC_SM_COUNT_FALLBACK;
   char err[512] = {0};
   int64_t launches = 0;
+  bool force_plain_spmv = false;   // MYC_FORCE_PLAIN_SPMV=1: use the non-TMA CSR-stream kernel
 
   // ---- scratch arenas (grown on demand, never shrunk)
   DevBuf scan_tmp;              // block sums of the exclusive scan (all levels)
@@ -42,6 +43,13 @@ struct myc_ctx {
   DevBuf lc[14];                // device copies owned by myc_load_case_host
   void* h_pinned = nullptr;     // 4 KB pinned staging for host scalars
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  // ---- sampled per-launch timing of the fused SpMV (bench.py roofline; off by default)
+  static constexpr int PROF_PAIRS = 128;
+  bool prof_on = false;
+  cudaEvent_t prof_ev[2 * PROF_PAIRS] = {nullptr};
+  double prof_ms = 0.0, prof_bytes = 0.0;
+  int64_t prof_samples = 0, prof_launches = 0;
 
   // ---- assembly plan retained between symbolic and numeric
   bool plan_valid = false;

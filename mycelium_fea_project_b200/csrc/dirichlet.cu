@@ -4,6 +4,7 @@
 // used for structure parity (:118).
 #include "common.cuh"
 #include "spmv.cuh"
+#include "spmv_tma.cuh"
 
 namespace {
 
@@ -179,11 +180,9 @@ extern "C" int myc_apply_dirichlet(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_
   }
   jacobi_kernel<<<g_rows, DI_THREADS, 0, st>>>(n_rows, row_offset, d_row_ptr, d_col_idx, d_val, reg, d_out_dinv);
   MYC_LAUNCHED(ctx);
-  const int grid = grid_for(ctx, ceil_div64(n_rows, SP_ROWS), SP_BLOCKS_PER_SM);
   EpiRhs epi{d_out_rhs, d_out_dinv};
-  myc_spmv_kernel<EpiRhs><<<grid, SP_THREADS, 0, st>>>(n_rows, d_row_ptr, d_col_idx, d_val, d_out_ubc, epi,
-                                                       nullptr, nullptr, nullptr, nullptr);
-  MYC_LAUNCHED(ctx);
+  MYC_TRY(myc_launch_spmv_epi<EpiRhs>(ctx, n_rows, d_row_ptr, d_col_idx, d_val, d_out_ubc, epi, nullptr, nullptr,
+                                      nullptr, nullptr, st));
   int* h = (int*)ctx->h_pinned;
   MYC_CUDA(ctx, cudaMemcpyAsync(h, bad_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   MYC_CUDA(ctx, cudaStreamSynchronize(st));

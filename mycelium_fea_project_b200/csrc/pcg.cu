@@ -15,6 +15,7 @@
 // NCCL all-reduced in place and p's halo is refreshed before each SpMV.
 #include "common.cuh"
 #include "spmv.cuh"
+#include "spmv_tma.cuh"
 
 int myc_dist_allreduce_dev(myc_ctx* ctx, double* d_buf, int n, cudaStream_t st);   // dist.cu
 int myc_dist_halo(myc_ctx* ctx, double* d_x_global, cudaStream_t st);              // dist.cu
@@ -202,11 +203,8 @@ struct HostScalars {  // pinned mirror
 int myc_launch_spmv(myc_ctx* ctx, int64_t n_rows, const int32_t* rp, const int32_t* ci,
                     const double* v, const double* x, double* y, cudaStream_t st) {
   if (n_rows == 0) return MYC_OK;
-  const int grid = grid_for(ctx, ceil_div64(n_rows, SP_ROWS), SP_BLOCKS_PER_SM);
   EpiPlain epi{y};
-  myc_spmv_kernel<EpiPlain><<<grid, SP_THREADS, 0, st>>>(n_rows, rp, ci, v, x, epi, nullptr, nullptr, nullptr, nullptr);
-  MYC_LAUNCHED(ctx);
-  return MYC_OK;
+  return myc_launch_spmv_epi<EpiPlain>(ctx, n_rows, rp, ci, v, x, epi, nullptr, nullptr, nullptr, nullptr, st);
 }
 
 extern "C" int myc_spmv(myc_ctx* ctx, int64_t n_rows, const int32_t* d_row_ptr, const int32_t* d_col_idx,
@@ -242,11 +240,9 @@ static int launch_residual(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, 
     MYC_LAUNCHED(ctx);
   }
   if (ctx->world > 1) MYC_TRY(myc_dist_halo(ctx, pg, st));
-  const int grid = grid_for(ctx, ceil_div64(n_rows, SP_ROWS), SP_BLOCKS_PER_SM);
   EpiResid epi{r_out, b, dinv, pg, row_offset, reg};
-  myc_spmv_kernel<EpiResid><<<grid, SP_THREADS, 0, st>>>(n_rows, rp, ci, v, pg, epi, (double*)ctx->partials.p,
-                                                         &sc->counter, &sc->out[0], nullptr);
-  MYC_LAUNCHED(ctx);
+  MYC_TRY(myc_launch_spmv_epi<EpiResid>(ctx, n_rows, rp, ci, v, pg, epi, (double*)ctx->partials.p, &sc->counter,
+                                        &sc->out[0], nullptr, st));
   if (ctx->world > 1) MYC_TRY(myc_dist_allreduce_dev(ctx, &sc->out[0], 2, st));
   return MYC_OK;
 }
@@ -274,7 +270,6 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   PcgScalars* h_sc = (PcgScalars*)ctx->h_pinned;       // two pinned slots, 512 B apart
   const bool dist = ctx->world > 1;
 
-  const int sgrid = grid_for(ctx, ceil_div64(n_rows, SP_ROWS), SP_BLOCKS_PER_SM);
   const int64_t vec_items = block3 ? n_rows / 3 : n_rows;
   const int vgrid = grid_for(ctx, ceil_div64(vec_items, VEC_THREADS), 8);
   const int dgrid = grid_for(ctx, ceil_div64(n_rows, VEC_THREADS), 8);
@@ -298,6 +293,7 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   const int64_t chunk = 32;
   int64_t it = 0;
   int64_t n_snap = 0;
+  int prof_used = 0;
   PcgScalars last{};
   for (;;) {
     const int64_t upto = (it + chunk < maxit) ? it + chunk : maxit;
@@ -306,9 +302,11 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       MYC_LAUNCHED(ctx);
       if (dist) MYC_TRY(myc_dist_halo(ctx, pg, st));
       EpiCgAp epi{Ap, pg, row_offset, reg};
-      myc_spmv_kernel<EpiCgAp><<<sgrid, SP_THREADS, 0, st>>>(n_rows, d_row_ptr, d_col_idx, d_val, pg, epi,
-                                                             partials, &sc->counter, &sc->pAp, &sc->done);
-      MYC_LAUNCHED(ctx);
+      const bool sample = ctx->prof_on && (it % 32) == 8 && prof_used < myc_ctx::PROF_PAIRS;
+      if (sample) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[2 * prof_used], st));
+      MYC_TRY(myc_launch_spmv_epi<EpiCgAp>(ctx, n_rows, d_row_ptr, d_col_idx, d_val, pg, epi, partials, &sc->counter,
+                                           &sc->pAp, &sc->done, st));
+      if (sample) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[2 * prof_used++ + 1], st));
       if (dist) MYC_TRY(myc_dist_allreduce_dev(ctx, &sc->pAp, 1, st));
       if (block3)
         pcg_update_kernel<true><<<vgrid, VEC_THREADS, 0, st>>>(n_rows, row_offset, pg, Ap, d_dinv, d_binv, d_x, r, zv, partials, sc);
@@ -336,6 +334,25 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   }
   MYC_CUDA(ctx, cudaStreamSynchronize(st));
   if (!last.done && n_snap >= 1) last = *(const PcgScalars*)((const char*)h_sc + 512 * ((n_snap - 1) & 1));
+  if (ctx->prof_on) {
+    // only launches that ran before convergence did the work (later ones return immediately)
+    const int64_t live = last.done ? (int64_t)last.iters : it;
+    int64_t nnz_local = 0;
+    {
+      int32_t h_nnz = 0;
+      MYC_CUDA(ctx, cudaMemcpy(&h_nnz, d_row_ptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost));
+      nnz_local = h_nnz;
+    }
+    for (int k = 0; k < prof_used; ++k) {
+      if ((int64_t)k * 32 + 8 >= live) break;
+      float ms = 0.f;
+      MYC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[2 * k], ctx->prof_ev[2 * k + 1]));
+      ctx->prof_ms += ms;
+      ctx->prof_bytes += 12.0 * (double)nnz_local + 20.0 * (double)n_rows;
+      ctx->prof_samples++;
+    }
+    ctx->prof_launches += live;
+  }
   const double relres = last.bb > 0.0 ? sqrt(last.red[1] / last.bb) : 0.0;
   if (h_out_iters) *h_out_iters = last.done ? (int64_t)last.iters : it;
   if (h_out_relres) *h_out_relres = relres;

@@ -1,0 +1,229 @@
+// TMA-pipelined CSR SpMV (sm_100a).  The plain CSR-stream kernel (spmv.cuh) was measured at
+// 3.7 TB/s on the 2048^2 operator with 73 % of warp stalls on the global-load scoreboard
+// (profiles/r1_spmv2048_ncu.md): not enough bytes in flight.  Here every WARP runs its own
+// asynchronous pipeline over a contiguous range of 32-row tiles:
+//
+//   lane 0:  cp.async.bulk (1-D TMA, SASS UBLKCP) of the tile's value and column windows into
+//            a 3-stage shared-memory ring, completion on a per-stage mbarrier (expect_tx)
+//   warp  :  waits the stage, forms products val*x[col] in place (lanes stride the nnz window,
+//            so x gathers of the 3 DOFs of a node coalesce), __syncwarp, one lane per row sums
+//            its products left to right (fixed order => bit-reproducible), epilogue, refill.
+//
+// There is no __syncthreads in the loop: warps drift apart freely, two tiles per warp are always
+// in flight (8 warps x 2 x ~4.2 KB ~ 67 KB per SM), and the streamed matrix bypasses L1 and the
+// register file.  Windows are widened to 16-byte boundaries as cp.async.bulk requires; the <=3
+// leading elements belong to the previous tile and are ignored, the ragged end of the whole
+// array is fetched with plain loads.  Tiles whose window exceeds the stage (rows much denser than
+// this problem's 3*(neighbours+1)) are computed straight from global memory.
+#pragma once
+#include "common.cuh"
+#include "spmv.cuh"
+
+constexpr int TM_WARPS = 8;
+constexpr int TM_THREADS = 32 * TM_WARPS;
+constexpr int TM_ROWS = 32;          // rows per warp tile (one per lane in the sum phase)
+constexpr int TM_CAP = 512;          // elements per stage window (16 nnz/row on average + padding)
+constexpr int TM_STAGES = 3;
+constexpr size_t TM_SMEM_PER_WARP = (size_t)TM_STAGES * TM_CAP * (sizeof(double) + sizeof(int32_t));
+constexpr size_t TM_SMEM_BYTES = TM_WARPS * TM_SMEM_PER_WARP + TM_WARPS * TM_STAGES * sizeof(uint64_t) + 128;
+
+__device__ __forceinline__ uint32_t tm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tm_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tm_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tm_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tm_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(tm_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tm_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    if (++spins > (1u << 22)) __trap();   // a lost TMA completion must fail loudly, not hang the GPU
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(tm_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tm_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <class Epi>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_t* __restrict__ ci,
+                    const double* __restrict__ v, const double* __restrict__ x, Epi epi, double* partials,
+                    unsigned* counter, double* out, const int* done) {
+  extern __shared__ __align__(128) unsigned char tm_smem[];
+  __shared__ double s_warp[TM_THREADS / 32];
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* s_val = reinterpret_cast<double*>(tm_smem) + (size_t)warp * TM_STAGES * TM_CAP;
+  int32_t* s_col = reinterpret_cast<int32_t*>(tm_smem + (size_t)TM_WARPS * TM_STAGES * TM_CAP * sizeof(double)) +
+                   (size_t)warp * TM_STAGES * TM_CAP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tm_smem + TM_WARPS * TM_SMEM_PER_WARP) + warp * TM_STAGES;
+
+  double acc[Epi::NACC == 0 ? 1 : Epi::NACC];
+#pragma unroll
+  for (int j = 0; j < (Epi::NACC == 0 ? 1 : Epi::NACC); ++j) acc[j] = 0.0;
+
+  // contiguous range of warp tiles for this warp
+  const int64_t n_tiles = (n_rows + TM_ROWS - 1) / TM_ROWS;
+  const int64_t n_warps = (int64_t)gridDim.x * TM_WARPS;
+  const int64_t gw = (int64_t)blockIdx.x * TM_WARPS + warp;
+  const int64_t per = n_tiles / n_warps, rem = n_tiles % n_warps;
+  const int64_t t_begin = gw * per + (gw < rem ? gw : rem);
+  const int64_t t_count = per + (gw < rem ? 1 : 0);
+  const int32_t nnz_total = rp[n_rows];
+  const int32_t nnz4 = nnz_total & ~3;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < TM_STAGES; ++s) tm_mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  auto tile_lo = [&](int64_t t) -> int32_t {   // first nnz of tile t (t may be one past the end)
+    const int64_t r = t * TM_ROWS;
+    return rp[r < n_rows ? r : n_rows];
+  };
+  // issue the TMA loads of one tile into stage s; returns whether loads were issued
+  auto issue = [&](int s, int32_t lo, int32_t hi) {
+    const int32_t a0 = lo & ~3;
+    int32_t a1 = (hi + 3) & ~3;
+    if (a1 > nnz4) a1 = nnz4;                    // never read past the arrays
+    const int32_t n = a1 - a0;
+    if (hi > lo && hi - a0 <= TM_CAP && n > 0) {
+      tm_mbar_expect_tx(&bars[s], (uint32_t)n * 12u);
+      tm_bulk_load(s_val + (size_t)s * TM_CAP, v + a0, (uint32_t)n * 8u, &bars[s]);
+      tm_bulk_load(s_col + (size_t)s * TM_CAP, ci + a0, (uint32_t)n * 4u, &bars[s]);
+    }
+  };
+
+  // prologue: tiles 0 .. STAGES-2 in flight, boundaries of the next tile to issue in registers
+  int32_t iss_lo = 0, iss_hi = 0;
+  if (t_count > 0) {
+    for (int s = 0; s < TM_STAGES - 1 && s < t_count; ++s) {
+      const int32_t lo = tile_lo(t_begin + s), hi = tile_lo(t_begin + s + 1);
+      if (lane == 0) issue(s, lo, hi);
+    }
+    if (TM_STAGES - 1 < t_count) {
+      iss_lo = tile_lo(t_begin + TM_STAGES - 1);
+      iss_hi = tile_lo(t_begin + TM_STAGES);
+    }
+  }
+  uint32_t phase_bits = 0;
+  // row pointers of tile j (rp_cur) and tile j+1 (rp_nxt) live in registers; tile j+2's are
+  // requested at the top of iteration j, so no global-load latency sits on the critical path
+  int32_t rp_cur = 0, rp_nxt = 0;
+  if (t_count > 0) {
+    const int64_t r = t_begin * TM_ROWS + lane;
+    rp_cur = rp[r < n_rows ? r : n_rows];
+    rp_nxt = rp[r + TM_ROWS < n_rows ? r + TM_ROWS : n_rows];
+  }
+
+  for (int64_t j = 0; j < t_count; ++j) {
+    const int s = (int)(j % TM_STAGES);
+    const int64_t t = t_begin + j;
+    // refill the stage tile j-1 has just released with tile j+STAGES-1
+    if (j + TM_STAGES - 1 < t_count) {
+      if (lane == 0) issue((int)((j + TM_STAGES - 1) % TM_STAGES), iss_lo, iss_hi);
+      if (j + TM_STAGES < t_count) {             // boundaries for the refill of the next iteration
+        iss_lo = iss_hi;
+        iss_hi = tile_lo(t + TM_STAGES + 1);
+      }
+    }
+    const int64_t r0 = t * TM_ROWS;
+    int32_t rp_nn;
+    {
+      const int64_t r = r0 + 2 * TM_ROWS + lane;
+      rp_nn = rp[r < n_rows ? r : n_rows];
+    }
+    const int32_t lo = __shfl_sync(0xffffffffu, rp_cur, 0);
+    const int32_t hi = __shfl_sync(0xffffffffu, rp_nxt, 0);
+    int32_t my_lo = rp_cur;
+    int32_t my_hi = __shfl_down_sync(0xffffffffu, rp_cur, 1);
+    if (lane == 31) my_hi = hi;
+    const bool row_ok = (r0 + lane) < n_rows;
+    const int32_t a0 = lo & ~3;
+    double sum = 0.0;
+    if (hi > lo) {
+      if (hi - a0 <= TM_CAP) {
+        double* sv = s_val + (size_t)s * TM_CAP;
+        const int32_t* sc = s_col + (size_t)s * TM_CAP;
+        int32_t a1 = (hi + 3) & ~3;
+        if (a1 > nnz4) a1 = nnz4;
+        if (a1 > a0) {
+          tm_mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+          phase_bits ^= (1u << s);
+        }
+        const int first = lo - a0, last = hi - a0, staged = a1 - a0;
+        int k = first + lane;
+#pragma unroll 4
+        for (; k < last; k += 32) {
+          double a;
+          int32_t c;
+          if (k < staged) { a = sv[k]; c = sc[k]; }
+          else { a = v[a0 + k]; c = ci[a0 + k]; }          // ragged end of the whole array (<4 elements)
+          sv[k] = a * __ldg(x + c);
+        }
+        __syncwarp();
+        if (row_ok) {
+          const int e = my_hi - a0;
+          for (int q = my_lo - a0; q < e; ++q) sum += sv[q];
+        }
+        // every lane orders its generic-proxy accesses to this stage before the async-proxy
+        // refill that lane 0 issues after the warp barrier
+        tm_fence_proxy_async();
+        __syncwarp();
+      } else if (row_ok) {
+        // oversize tile: lane-per-row straight from global memory (left-to-right, deterministic)
+        for (int32_t q = my_lo; q < my_hi; ++q) sum += v[q] * __ldg(x + ci[q]);
+      }
+    }
+    if (row_ok) epi.row(r0 + lane, sum, acc);
+    rp_cur = rp_nxt;
+    rp_nxt = rp_nn;
+  }
+
+  if constexpr (Epi::NACC > 0) {
+#pragma unroll
+    for (int j = 0; j < Epi::NACC; ++j) acc[j] = myc_block_reduce(acc[j], s_warp);
+    myc_finalize_partials<Epi::NACC>(partials, acc, counter, out, s_warp);
+  }
+}
+
+// Launch helper: TMA kernel when the arrays are 16-byte aligned (always true for torch / cudaMalloc
+// buffers), the plain CSR-stream kernel otherwise.
+template <class Epi>
+static inline int myc_launch_spmv_epi(myc_ctx* ctx, int64_t n_rows, const int32_t* rp, const int32_t* ci,
+                                      const double* v, const double* x, const Epi& epi, double* partials,
+                                      unsigned* counter, double* out, const int* done, cudaStream_t st) {
+  if (n_rows == 0) return MYC_OK;
+  const bool aligned = (((uintptr_t)ci | (uintptr_t)v) & 15u) == 0;
+  if (aligned && !ctx->force_plain_spmv) {
+    static bool attr_set = false;   // per template instantiation
+    if (!attr_set) {
+      MYC_CUDA(ctx, cudaFuncSetAttribute(myc_spmv_tma_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TM_SMEM_BYTES));
+      attr_set = true;
+    }
+    const int64_t n_tiles = ceil_div64(n_rows, TM_ROWS);
+    const int grid = grid_for(ctx, ceil_div64(n_tiles, TM_WARPS), 1);
+    myc_spmv_tma_kernel<Epi><<<grid, TM_THREADS, TM_SMEM_BYTES, st>>>(n_rows, rp, ci, v, x, epi, partials, counter,
+                                                                      out, done);
+  } else {
+    const int grid = grid_for(ctx, ceil_div64(n_rows, SP_ROWS), SP_BLOCKS_PER_SM);
+    myc_spmv_kernel<Epi><<<grid, SP_THREADS, 0, st>>>(n_rows, rp, ci, v, x, epi, partials, counter, out, done);
+  }
+  MYC_LAUNCHED(ctx);
+  return MYC_OK;
+}

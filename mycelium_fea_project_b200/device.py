@@ -87,7 +87,8 @@ class DeviceMesh:
         if n1h.size and (min(n1h.min(), n2h.min()) < 0 or max(n1h.max(), n2h.max()) >= n_nodes):
             raise IndexError("element end node outside [0, n_nodes)")     # numpy would raise too (:82-83)
         def up(a, dt):
-            t = torch.from_numpy(np.ascontiguousarray(a, dtype=dt))
+            arr = np.ascontiguousarray(a, dtype=dt)
+            t = torch.from_numpy(arr if arr.flags.writeable else arr.copy())
             if pinned:
                 t = t.pin_memory()
             return t.to(dev, non_blocking=pinned)

@@ -1,0 +1,197 @@
+"""Row-partitioned multi-GPU solve: one process per GPU, NCCL over NVLink.
+
+Partition (the PETSc MPIAIJ layout of src/fea_petsc_parallel.cpp:236, at node granularity):
+rank r owns the contiguous node range [offsets[r], offsets[r+1]) and therefore DOF rows
+[3*offsets[r], 3*offsets[r+1]).  Each rank assembles ONLY its rows, from the elements incident
+to its nodes (elements crossing a cut are evaluated on both sides; K_e is cheap), so assembly
+needs no communication -- and none of the reference's P-fold over-assembly
+(src/fea_petsc_parallel.cpp:242-265).
+
+Vectors gathered through column indices are kept at global length on every rank, so a halo
+refresh is a send/recv of contiguous DOF ranges between the peers' buffers at identical
+offsets (csrc/dist.cu).  The plan below (which ranges) is plain numpy and is exercised on CPU
+with gloo (tests/test_dist_cpu.py); the exchange inside the solver runs in the C library on
+NCCL.  Meshes whose node numbering is not spatially local should be renumbered first
+(``locality_order``), otherwise the ranges degenerate to whole partitions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------------------------
+# plan (pure numpy -- no CUDA, no torch)
+# ---------------------------------------------------------------------------------------------
+def partition_nodes(n_nodes: int, world: int) -> np.ndarray:
+    """Balanced contiguous node ranges: offsets[world+1] (first n_nodes % world ranks get one more,
+    PETSC_DECIDE's rule applied to nodes instead of rows)."""
+    base, rem = divmod(int(n_nodes), int(world))
+    sizes = np.full(world, base, dtype=np.int64)
+    sizes[:rem] += 1
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+def owner_of(nodes, offsets):
+    return np.searchsorted(offsets, nodes, side="right") - 1
+
+
+def halo_ranges(n1, n2, active, offsets, rank):
+    """For ``rank``: per peer q the half-open node range [lo, hi) of q's nodes that appear as
+    the far end of an active element with a near end owned by ``rank`` (lo == hi: nothing)."""
+    world = len(offsets) - 1
+    n1 = np.asarray(n1, dtype=np.int64)
+    n2 = np.asarray(n2, dtype=np.int64)
+    if active is not None:
+        m = np.asarray(active).astype(bool)
+        n1, n2 = n1[m], n2[m]
+    lo = np.zeros(world, dtype=np.int64)
+    hi = np.zeros(world, dtype=np.int64)
+    b, e = offsets[rank], offsets[rank + 1]
+    far = np.concatenate([n2[(n1 >= b) & (n1 < e)], n1[(n2 >= b) & (n2 < e)]])
+    far = far[(far < b) | (far >= e)]
+    if far.size:
+        own = owner_of(far, offsets)
+        for q in np.unique(own):
+            f = far[own == q]
+            lo[q], hi[q] = f.min(), f.max() + 1
+    return lo, hi
+
+
+def locality_order(coords, axis=1):
+    """Permutation that numbers nodes along ``axis`` (ties by the other in-plane axis) so that
+    contiguous ranges are spatial strips.  perm[new] = old."""
+    c = np.asarray(coords)
+    other = 0 if axis == 1 else 1
+    return np.lexsort((c[:, other], c[:, axis]))
+
+
+@dataclass
+class HaloPlan:
+    rank: int
+    world: int
+    offsets: np.ndarray      # (world+1,) node offsets
+    need_lo: np.ndarray      # (world,) node ranges this rank receives from q
+    need_hi: np.ndarray
+    give_lo: np.ndarray      # (world,) node ranges this rank sends to q
+    give_hi: np.ndarray
+
+    @property
+    def node_begin(self):
+        return int(self.offsets[self.rank])
+
+    @property
+    def node_end(self):
+        return int(self.offsets[self.rank + 1])
+
+
+def make_plan(n1, n2, active, n_nodes, rank, world, all_gather=None) -> HaloPlan:
+    """Build this rank's plan.  ``all_gather(array) -> list of arrays`` exchanges the need
+    table between ranks (torch.distributed in production); if None, every rank's needs are
+    computed locally (all ranks hold the whole mesh, so this is equivalent, just O(world) more
+    host work)."""
+    offsets = partition_nodes(n_nodes, world)
+    lo, hi = halo_ranges(n1, n2, active, offsets, rank)
+    if all_gather is not None:
+        table = all_gather(np.stack([lo, hi]))
+    else:
+        table = [np.stack(halo_ranges(n1, n2, active, offsets, q)) for q in range(world)]
+    give_lo = np.array([table[q][0][rank] for q in range(world)], dtype=np.int64)
+    give_hi = np.array([table[q][1][rank] for q in range(world)], dtype=np.int64)
+    return HaloPlan(rank, world, offsets, lo, hi, give_lo, give_hi)
+
+
+def exchange_halo_torch(x_global, plan: HaloPlan, group=None):
+    """Reference halo refresh with torch.distributed point-to-point ops (works on gloo and
+    nccl).  Same semantics as myc_halo_exchange; used by the CPU tests."""
+    import torch.distributed as dist
+    ops = []
+    for q in range(plan.world):
+        if q == plan.rank:
+            continue
+        if plan.give_hi[q] > plan.give_lo[q]:
+            ops.append(dist.P2POp(dist.isend, x_global[3 * plan.give_lo[q]:3 * plan.give_hi[q]], q, group))
+        if plan.need_hi[q] > plan.need_lo[q]:
+            ops.append(dist.P2POp(dist.irecv, x_global[3 * plan.need_lo[q]:3 * plan.need_hi[q]], q, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return x_global
+
+
+# ---------------------------------------------------------------------------------------------
+# production path: C library + NCCL
+# ---------------------------------------------------------------------------------------------
+class DistributedSolver:
+    """Collective driver of one load case on a row-partitioned mesh.  Every rank holds the whole
+    (small) mesh description; matrices and solver vectors are partitioned."""
+
+    def __init__(self, mesh_host, active=None, device=None):
+        import torch
+        import torch.distributed as dist
+        from . import device as dv
+        from ._lib import lib, check, nccl_library_path
+        coords, n1, n2 = mesh_host
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.ctx = dv.Context.get(device)
+        self.n_nodes = int(len(coords))
+
+        def all_gather(arr):
+            out = [None] * self.world
+            dist.all_gather_object(out, arr)
+            return out
+
+        self.plan = make_plan(n1, n2, active, self.n_nodes, self.rank, self.world, all_gather)
+        self.mesh = dv.DeviceMesh.from_host(coords, n1, n2, active, device=self.ctx.device)
+        if self.world > 1 and self.ctx.world == 1:
+            path = nccl_library_path().encode()
+            uid = np.zeros(128, dtype=np.uint8)
+            if self.rank == 0:
+                rc = lib.myc_dist_unique_id(path, uid.ctypes.data_as(C.c_void_p))
+                if rc != 0:
+                    raise RuntimeError("myc_dist_unique_id failed (NCCL not loadable)")
+            t = torch.from_numpy(uid).to(self.ctx.device)
+            dist.broadcast(t, 0)
+            uid = t.cpu().numpy()
+            p = self.plan
+            check(self.ctx.h, lib.myc_dist_init(
+                self.ctx.h, path, uid.ctypes.data_as(C.c_void_p), self.rank, self.world,
+                p.offsets.ctypes.data_as(C.c_void_p), p.need_lo.ctypes.data_as(C.c_void_p),
+                p.need_hi.ctypes.data_as(C.c_void_p)))
+            self.ctx.rank, self.ctx.world = self.rank, self.world
+            self.ctx.node_offsets = p.offsets
+
+    def assemble(self, E, A, I):
+        from . import device as dv
+        return dv.assemble(self.ctx, self.mesh, E, A, I, node_range=(self.plan.node_begin, self.plan.node_end))
+
+    def load_case(self, K, known_dofs, known_vals, react_dofs=None, rtol=1e-10, precond="jacobi",
+                  maxit=2_000_000, reg=1e-12, gather_U=True):
+        """Returns dict(U (global, on every rank if gather_U), iterations, relres, total_force)."""
+        import torch
+        from . import device as dv
+        from ._lib import lib, check
+        ctx = self.ctx
+        dev = ctx.device
+        td = lambda a, dt: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+        kd, kv = td(known_dofs, np.int64), td(known_vals, np.float64)
+        sysd = dv.apply_dirichlet(ctx, K, kd, kv, reg, block3=(precond == "block3"))
+        x, iters, relres = dv.pcg(ctx, K, sysd, precond=precond, rtol=rtol, maxit=maxit)
+        U = dv.merge_solution(ctx, K, sysd, x)         # own rows of a zeroed global vector
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        total_force = None
+        if gather_U or react_dofs is not None:
+            if self.world > 1:
+                check(ctx.h, lib.myc_allgather_owned(ctx.h, C.c_void_p(U.data_ptr()), stream))
+        if react_dofs is not None:
+            rd = np.asarray(react_dofs, dtype=np.int64)
+            lo, hi = K.row_offset, K.row_offset + K.n_rows
+            mine = rd[(rd >= lo) & (rd < hi)] - lo
+            F = dv.spmv(ctx, K, U)                      # local rows of K @ U   (fea_solver.py:257)
+            part = dv.gather_sum(ctx, F, td(mine, np.int64)) if len(mine) else 0.0
+            buf = (C.c_double * 1)(part)
+            check(ctx.h, lib.myc_allreduce_sum(ctx.h, buf, 1, stream))
+            total_force = float(buf[0])
+        return {"U": U, "x": x, "system": sysd, "iterations": iters, "relres": relres, "total_force": total_force}

@@ -57,7 +57,8 @@ def _ctx():
 
 
 def _dev(a, dtype):
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(_ctx().device)
+    arr = np.ascontiguousarray(a, dtype=dtype)
+    return torch.from_numpy(arr if arr.flags.writeable else arr.copy()).to(_ctx().device)
 
 
 # ---------------------------------------------------------------------------------------------

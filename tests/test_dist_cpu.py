@@ -1,0 +1,144 @@
+"""world_size-2/3 CPU tests (gloo) of the multi-GPU host logic: partition, halo-range plan, the
+halo exchange protocol and the row-partitioned PCG recurrences -- the same protocol
+csrc/dist.cu + csrc/pcg.cu run on NCCL.  The numerics here are numpy/scipy (the oracle's K);
+no CUDA is touched."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mycelium_fea_project_b200 import dist as md
+from mycelium_fea_project_b200.synth import synth_network
+from oracle import fea_oracle as fo
+
+
+def test_partition_and_plan_single_process():
+    coords, n1, n2 = synth_network(64)
+    n = len(coords)
+    for world in (1, 2, 3, 8):
+        off = md.partition_nodes(n, world)
+        assert off[0] == 0 and off[-1] == n and len(off) == world + 1
+        assert np.all(np.diff(off) >= n // world) and np.all(np.diff(off) <= n // world + 1)
+        K = fo.assemble_global_stiffness(coords, n1, n2, np.ones(len(n1), bool))
+        for r in range(world):
+            p = md.make_plan(n1, n2, None, n, r, world)
+            rows = K[3 * off[r]:3 * off[r + 1]]
+            cols = np.unique(rows.indices) // 3
+            ext = cols[(cols < off[r]) | (cols >= off[r + 1])]
+            # every external column node lies inside the range requested from its owner
+            own = md.owner_of(ext, off)
+            for q in np.unique(own):
+                e = ext[own == q]
+                assert p.need_lo[q] <= e.min() and e.max() < p.need_hi[q]
+                assert off[q] <= p.need_lo[q] and p.need_hi[q] <= off[q + 1]
+            # strip partition of a row-major grid: only the two neighbours are needed
+            assert set(np.nonzero(p.need_hi > p.need_lo)[0]) <= {r - 1, r + 1}
+            # give is the transpose of need
+            for q in range(world):
+                pq = md.make_plan(n1, n2, None, n, q, world)
+                assert p.give_lo[q] == pq.need_lo[r] and p.give_hi[q] == pq.need_hi[r]
+
+
+def test_locality_order_makes_ranges_small():
+    coords, n1, n2 = synth_network(32)
+    rng = np.random.default_rng(0)
+    shuffle = rng.permutation(len(coords))              # destroy the numbering
+    inv = np.empty_like(shuffle); inv[shuffle] = np.arange(len(shuffle))
+    c2, a2, b2 = coords[shuffle], inv[n1], inv[n2]
+    off = md.partition_nodes(len(c2), 4)
+    lo, hi = md.halo_ranges(a2, b2, None, off, 1)
+    assert (hi - lo).sum() > 0.5 * len(c2)              # all-to-all without reordering
+    perm = md.locality_order(c2, axis=1)
+    inv2 = np.empty_like(perm); inv2[perm] = np.arange(len(perm))
+    lo, hi = md.halo_ranges(inv2[a2], inv2[b2], None, off, 1)
+    assert (hi - lo).sum() < 0.15 * len(c2)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, N, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        coords, n1, n2 = synth_network(N)
+        n = len(coords)
+
+        def all_gather(arr):
+            out = [None] * world
+            dist.all_gather_object(out, arr)
+            return out
+
+        plan = md.make_plan(n1, n2, None, n, rank, world, all_gather)
+        plan_local = md.make_plan(n1, n2, None, n, rank, world)
+        assert np.array_equal(plan.give_lo, plan_local.give_lo) and np.array_equal(plan.give_hi, plan_local.give_hi)
+        K = fo.assemble_global_stiffness(coords, n1, n2, np.ones(len(n1), bool))
+        lo, hi = 3 * plan.node_begin, 3 * plan.node_end
+        Kloc = K[lo:hi]
+        # --- halo exchange: own slice valid, rest poisoned, then refreshed from the owners
+        xfull = np.random.default_rng(1).standard_normal(3 * n)
+        xg = torch.full((3 * n,), float("nan"), dtype=torch.float64)
+        xg[lo:hi] = torch.from_numpy(xfull[lo:hi])
+        md.exchange_halo_torch(xg, plan)
+        y = Kloc @ np.nan_to_num(xg.numpy(), nan=1e300)
+        assert np.array_equal(y, (K @ xfull)[lo:hi]), "halo did not cover every external column"
+        # --- row-partitioned Jacobi-PCG with the recurrences of csrc/pcg.cu
+        top, bot = fo.grip_nodes(coords, 0.5)
+        kd, kv = fo.build_bc(top, bot, 0.02, -0.02)
+        ubc = np.zeros(3 * n); ubc[kd] = kv
+        free = np.ones(3 * n, bool); free[kd] = False
+        fl = free[lo:hi]
+        b = np.where(fl, -(Kloc @ ubc), 0.0)
+        dinv = np.where(fl, 1.0 / (Kloc.diagonal(k=lo) + 1e-12), 0.0)
+
+        def allsum(*v):
+            t = torch.tensor(v, dtype=torch.float64)
+            dist.all_reduce(t)
+            return t.tolist()
+
+        x = np.zeros(hi - lo); r = b.copy()
+        pg = torch.zeros(3 * n, dtype=torch.float64)
+        pg[lo:hi] = torch.from_numpy(dinv * r)
+        (rz, bb) = allsum(float(r @ (dinv * r)), float(b @ b))
+        it = 0
+        while True:
+            md.exchange_halo_torch(pg, plan)
+            p = pg.numpy()
+            Ap = Kloc @ p + 1e-12 * p[lo:hi]
+            (pAp,) = allsum(float(p[lo:hi] @ Ap))
+            alpha = rz / pAp
+            x += alpha * p[lo:hi]
+            r = np.where(fl, r - alpha * Ap, 0.0)
+            it += 1
+            rz_new, rr = allsum(float(r @ (dinv * r)), float(r @ r))
+            if rr <= (1e-12 ** 2) * bb or it > 5000:
+                break
+            pg[lo:hi] = torch.from_numpy(dinv * r + (rz_new / rz) * p[lo:hi])
+            rz = rz_new
+        U = ubc.copy()
+        Uloc = np.where(fl, x, ubc[lo:hi])
+        gathered = all_gather(Uloc)
+        U = np.concatenate(gathered)
+        Uo = fo.solve_system(K, kd, kv)
+        err = np.linalg.norm(U - Uo) / np.linalg.norm(Uo)
+        assert err < 1e-8, err
+        ret[rank] = (it, err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_and_partitioned_pcg_gloo(world):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, 48, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    its = {v[0] for v in ret.values()}
+    assert len(its) == 1          # every rank took the same number of iterations
