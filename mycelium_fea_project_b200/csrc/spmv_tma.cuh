@@ -1,16 +1,17 @@
 // TMA-pipelined CSR SpMV (sm_100a).  The plain CSR-stream kernel (spmv.cuh) was measured at
 // 3.7 TB/s on the 2048^2 operator with 73 % of warp stalls on the global-load scoreboard
 // (profiles/r1_spmv2048_ncu.md): not enough bytes in flight.  Here every WARP runs its own
-// asynchronous pipeline over a contiguous range of 32-row tiles:
+// asynchronous pipeline over 32-row tiles (dealt round-robin over the grid's warps):
 //
 //   lane 0:  cp.async.bulk (1-D TMA, SASS UBLKCP) of the tile's value and column windows into
-//            a 3-stage shared-memory ring, completion on a per-stage mbarrier (expect_tx)
+//            a 2-stage shared-memory ring, completion on a per-stage mbarrier (expect_tx)
 //   warp  :  waits the stage, forms products val*x[col] in place (lanes stride the nnz window,
 //            so x gathers of the 3 DOFs of a node coalesce), __syncwarp, one lane per row sums
 //            its products left to right (fixed order => bit-reproducible), epilogue, refill.
 //
-// There is no __syncthreads in the loop: warps drift apart freely, two tiles per warp are always
-// in flight (8 warps x 2 x ~4.2 KB ~ 67 KB per SM), and the streamed matrix bypasses L1 and the
+// There is no __syncthreads in the loop: warps drift apart freely, every warp always has its
+// next tile in flight while it consumes the current one (16 warps x ~4.2 KB ~ 67 KB per SM in
+// flight), all x gathers of a tile are issued back to back, and the streamed matrix bypasses L1 and the
 // register file.  Windows are widened to 16-byte boundaries as cp.async.bulk requires; the <=3
 // leading elements belong to the previous tile and are ignored, the ragged end of the whole
 // array is fetched with plain loads.  Tiles whose window exceeds the stage (rows much denser than
@@ -19,11 +20,26 @@
 #include "common.cuh"
 #include "spmv.cuh"
 
+// Tunables (overridable with -D for tools/spmv_bench.cu sweeps)
+#ifndef TM_CFG_ROWS
+#define TM_CFG_ROWS 16
+#endif
+#ifndef TM_CFG_CAP
+#define TM_CFG_CAP 256
+#endif
+#ifndef TM_CFG_STAGES
+#define TM_CFG_STAGES 2
+#endif
+#ifndef TM_CFG_BLOCKS_PER_SM
+#define TM_CFG_BLOCKS_PER_SM 4
+#endif
 constexpr int TM_WARPS = 8;
 constexpr int TM_THREADS = 32 * TM_WARPS;
-constexpr int TM_ROWS = 32;          // rows per warp tile (one per lane in the sum phase)
-constexpr int TM_CAP = 512;          // elements per stage window (16 nnz/row on average + padding)
-constexpr int TM_STAGES = 3;
+constexpr int TM_ROWS = TM_CFG_ROWS;      // rows per warp tile (<= 32: one lane per row in the sum phase)
+constexpr int TM_CAP = TM_CFG_CAP;        // elements per stage window (16 nnz/row on average incl. padding)
+constexpr int TM_STAGES = TM_CFG_STAGES;
+constexpr int TM_BLOCKS_PER_SM = TM_CFG_BLOCKS_PER_SM;   // x TM_WARPS tile pipelines per SM
+static_assert(TM_ROWS >= 1 && TM_ROWS <= 32 && TM_CAP % 32 == 0, "tile shape");
 constexpr size_t TM_SMEM_PER_WARP = (size_t)TM_STAGES * TM_CAP * (sizeof(double) + sizeof(int32_t));
 constexpr size_t TM_SMEM_BYTES = TM_WARPS * TM_SMEM_PER_WARP + TM_WARPS * TM_STAGES * sizeof(uint64_t) + 128;
 
@@ -35,11 +51,13 @@ __device__ __forceinline__ void tm_mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void tm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tm_smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tm_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   tm_smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(tm_smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void tm_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                             uint64_t l2_policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          tm_smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(tm_smem_u32(bar)), "l"(l2_policy)
+      : "memory");
 }
 __device__ __forceinline__ void tm_mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
@@ -57,7 +75,7 @@ __device__ __forceinline__ void tm_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tm_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <class Epi>
-__global__ void __launch_bounds__(TM_THREADS, 1)
+__global__ void __launch_bounds__(TM_THREADS, TM_BLOCKS_PER_SM)
 myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_t* __restrict__ ci,
                     const double* __restrict__ v, const double* __restrict__ x, Epi epi, double* partials,
                     unsigned* counter, double* out, const int* done) {
@@ -74,15 +92,17 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
 #pragma unroll
   for (int j = 0; j < (Epi::NACC == 0 ? 1 : Epi::NACC); ++j) acc[j] = 0.0;
 
-  // contiguous range of warp tiles for this warp
+  // Tiles are dealt round-robin over all warps of the grid (tile = gw + j * n_warps): at any time
+  // the whole chip works inside one moving window of ~n_warps*32 rows, so the x entries gathered
+  // by neighbouring tiles are shared in L2/L1 instead of being spread over the whole vector.
   const int64_t n_tiles = (n_rows + TM_ROWS - 1) / TM_ROWS;
   const int64_t n_warps = (int64_t)gridDim.x * TM_WARPS;
   const int64_t gw = (int64_t)blockIdx.x * TM_WARPS + warp;
-  const int64_t per = n_tiles / n_warps, rem = n_tiles % n_warps;
-  const int64_t t_begin = gw * per + (gw < rem ? gw : rem);
-  const int64_t t_count = per + (gw < rem ? 1 : 0);
+  const int64_t t_count = gw < n_tiles ? (n_tiles - gw + n_warps - 1) / n_warps : 0;
   const int32_t nnz_total = rp[n_rows];
   const int32_t nnz4 = nnz_total & ~3;
+  uint64_t l2_stream;   // the matrix is read once per SpMV: evict-first, keep L2 for x
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
 
   if (lane == 0) {
 #pragma unroll
@@ -91,11 +111,13 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
   }
   __syncwarp();
 
-  auto tile_lo = [&](int64_t t) -> int32_t {   // first nnz of tile t (t may be one past the end)
-    const int64_t r = t * TM_ROWS;
-    return rp[r < n_rows ? r : n_rows];
+  // row pointers of tile t: lane l holds rp[32t + l] and rp[32t + l + 1] (clamped)
+  auto load_rp = [&](int64_t t, int32_t& lo_l, int32_t& hi_l) {
+    const int64_t r = t * TM_ROWS + (lane < TM_ROWS ? lane : TM_ROWS - 1);
+    lo_l = rp[r < n_rows ? r : n_rows];
+    hi_l = rp[r + 1 < n_rows ? r + 1 : n_rows];
   };
-  // issue the TMA loads of one tile into stage s; returns whether loads were issued
+  // issue the TMA loads of one tile [lo, hi) into stage s (lane 0 only)
   auto issue = [&](int s, int32_t lo, int32_t hi) {
     const int32_t a0 = lo & ~3;
     int32_t a1 = (hi + 3) & ~3;
@@ -103,62 +125,43 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
     const int32_t n = a1 - a0;
     if (hi > lo && hi - a0 <= TM_CAP && n > 0) {
       tm_mbar_expect_tx(&bars[s], (uint32_t)n * 12u);
-      tm_bulk_load(s_val + (size_t)s * TM_CAP, v + a0, (uint32_t)n * 8u, &bars[s]);
-      tm_bulk_load(s_col + (size_t)s * TM_CAP, ci + a0, (uint32_t)n * 4u, &bars[s]);
+      tm_bulk_load(s_val + (size_t)s * TM_CAP, v + a0, (uint32_t)n * 8u, &bars[s], l2_stream);
+      tm_bulk_load(s_col + (size_t)s * TM_CAP, ci + a0, (uint32_t)n * 4u, &bars[s], l2_stream);
     }
   };
 
-  // prologue: tiles 0 .. STAGES-2 in flight, boundaries of the next tile to issue in registers
-  int32_t iss_lo = 0, iss_hi = 0;
+  // Register pipeline of row pointers: tile j (cur), j+1 (nxt); tile j+2 is requested at the top
+  // of iteration j, so no global-load latency sits on the critical path.
+  int32_t cur_lo = 0, cur_hi = 0, nxt_lo = 0, nxt_hi = 0;
   if (t_count > 0) {
-    for (int s = 0; s < TM_STAGES - 1 && s < t_count; ++s) {
-      const int32_t lo = tile_lo(t_begin + s), hi = tile_lo(t_begin + s + 1);
-      if (lane == 0) issue(s, lo, hi);
-    }
-    if (TM_STAGES - 1 < t_count) {
-      iss_lo = tile_lo(t_begin + TM_STAGES - 1);
-      iss_hi = tile_lo(t_begin + TM_STAGES);
-    }
+    load_rp(gw, cur_lo, cur_hi);
+    if (t_count > 1) load_rp(gw + n_warps, nxt_lo, nxt_hi);
+    const int32_t lo = __shfl_sync(0xffffffffu, cur_lo, 0), hi = __shfl_sync(0xffffffffu, cur_hi, TM_ROWS - 1);
+    if (lane == 0) issue(0, lo, hi);
   }
   uint32_t phase_bits = 0;
-  // row pointers of tile j (rp_cur) and tile j+1 (rp_nxt) live in registers; tile j+2's are
-  // requested at the top of iteration j, so no global-load latency sits on the critical path
-  int32_t rp_cur = 0, rp_nxt = 0;
-  if (t_count > 0) {
-    const int64_t r = t_begin * TM_ROWS + lane;
-    rp_cur = rp[r < n_rows ? r : n_rows];
-    rp_nxt = rp[r + TM_ROWS < n_rows ? r + TM_ROWS : n_rows];
-  }
 
   for (int64_t j = 0; j < t_count; ++j) {
     const int s = (int)(j % TM_STAGES);
-    const int64_t t = t_begin + j;
-    // refill the stage tile j-1 has just released with tile j+STAGES-1
-    if (j + TM_STAGES - 1 < t_count) {
-      if (lane == 0) issue((int)((j + TM_STAGES - 1) % TM_STAGES), iss_lo, iss_hi);
-      if (j + TM_STAGES < t_count) {             // boundaries for the refill of the next iteration
-        iss_lo = iss_hi;
-        iss_hi = tile_lo(t + TM_STAGES + 1);
-      }
-    }
+    const int64_t t = gw + j * n_warps;
     const int64_t r0 = t * TM_ROWS;
-    int32_t rp_nn;
-    {
-      const int64_t r = r0 + 2 * TM_ROWS + lane;
-      rp_nn = rp[r < n_rows ? r : n_rows];
+    // refill the stage tile j-1 has just released with tile j+1
+    if (j + 1 < t_count) {
+      const int32_t lo1 = __shfl_sync(0xffffffffu, nxt_lo, 0), hi1 = __shfl_sync(0xffffffffu, nxt_hi, TM_ROWS - 1);
+      if (lane == 0) issue((int)((j + 1) % TM_STAGES), lo1, hi1);
     }
-    const int32_t lo = __shfl_sync(0xffffffffu, rp_cur, 0);
-    const int32_t hi = __shfl_sync(0xffffffffu, rp_nxt, 0);
-    int32_t my_lo = rp_cur;
-    int32_t my_hi = __shfl_down_sync(0xffffffffu, rp_cur, 1);
-    if (lane == 31) my_hi = hi;
-    const bool row_ok = (r0 + lane) < n_rows;
+    int32_t nn_lo = 0, nn_hi = 0;
+    if (j + 2 < t_count) load_rp(t + 2 * n_warps, nn_lo, nn_hi);
+    const int32_t lo = __shfl_sync(0xffffffffu, cur_lo, 0);
+    const int32_t hi = __shfl_sync(0xffffffffu, cur_hi, TM_ROWS - 1);
+    const int32_t my_lo = cur_lo, my_hi = cur_hi;
+    const bool row_ok = lane < TM_ROWS && (r0 + lane) < n_rows;
     const int32_t a0 = lo & ~3;
     double sum = 0.0;
     if (hi > lo) {
       if (hi - a0 <= TM_CAP) {
         double* sv = s_val + (size_t)s * TM_CAP;
-        const int32_t* sc = s_col + (size_t)s * TM_CAP;
+        int32_t* sc = s_col + (size_t)s * TM_CAP;
         int32_t a1 = (hi + 3) & ~3;
         if (a1 > nnz4) a1 = nnz4;
         if (a1 > a0) {
@@ -166,19 +169,36 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
           phase_bits ^= (1u << s);
         }
         const int first = lo - a0, last = hi - a0, staged = a1 - a0;
-        int k = first + lane;
-#pragma unroll 4
-        for (; k < last; k += 32) {
-          double a;
-          int32_t c;
-          if (k < staged) { a = sv[k]; c = sc[k]; }
-          else { a = v[a0 + k]; c = ci[a0 + k]; }          // ragged end of the whole array (<4 elements)
-          sv[k] = a * __ldg(x + c);
+        if (staged < last) {                      // ragged end of the whole array (< 4 elements)
+          const int k = (staged > first ? staged : first) + lane;
+          if (k < last) { sv[k] = v[a0 + k]; sc[k] = ci[a0 + k]; }
+          __syncwarp();
+        }
+        // products in place; fully unrolled so that every x gather of the tile is in flight at once
+        constexpr int TM_MAXIT = TM_CAP / 32;
+        int32_t c[TM_MAXIT];
+        double xv[TM_MAXIT];
+#pragma unroll
+        for (int u = 0; u < TM_MAXIT; ++u) {
+          const int k = first + lane + 32 * u;
+          c[u] = k < last ? sc[k] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < TM_MAXIT; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < TM_MAXIT; ++u) {
+          const int k = first + lane + 32 * u;
+          if (c[u] >= 0) sv[k] = sv[k] * xv[u];
         }
         __syncwarp();
         if (row_ok) {
+          int q = my_lo - a0;
           const int e = my_hi - a0;
-          for (int q = my_lo - a0; q < e; ++q) sum += sv[q];
+          for (; q + 3 < e; q += 4) {             // 4 independent loads, adds kept in row order
+            const double p0 = sv[q], p1 = sv[q + 1], p2 = sv[q + 2], p3 = sv[q + 3];
+            sum = (((sum + p0) + p1) + p2) + p3;
+          }
+          for (; q < e; ++q) sum += sv[q];
         }
         // every lane orders its generic-proxy accesses to this stage before the async-proxy
         // refill that lane 0 issues after the warp barrier
@@ -190,8 +210,8 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
       }
     }
     if (row_ok) epi.row(r0 + lane, sum, acc);
-    rp_cur = rp_nxt;
-    rp_nxt = rp_nn;
+    cur_lo = nxt_lo; cur_hi = nxt_hi;
+    nxt_lo = nn_lo; nxt_hi = nn_hi;
   }
 
   if constexpr (Epi::NACC > 0) {
@@ -217,7 +237,7 @@ static inline int myc_launch_spmv_epi(myc_ctx* ctx, int64_t n_rows, const int32_
       attr_set = true;
     }
     const int64_t n_tiles = ceil_div64(n_rows, TM_ROWS);
-    const int grid = grid_for(ctx, ceil_div64(n_tiles, TM_WARPS), 1);
+    const int grid = grid_for(ctx, ceil_div64(n_tiles, TM_WARPS), TM_BLOCKS_PER_SM);
     myc_spmv_tma_kernel<Epi><<<grid, TM_THREADS, TM_SMEM_BYTES, st>>>(n_rows, rp, ci, v, x, epi, partials, counter,
                                                                       out, done);
   } else {
