@@ -39,6 +39,7 @@ sys.path.insert(0, ROOT)
 GRIP = 1.5
 DISP = 0.02
 RTOL = 1e-10
+MAXIT = 400_000      # bound on PCG iterations (a mis-set problem must not burn GPU minutes)
 
 
 def specimen(case, grid, n_gpus, seed=0):
@@ -193,7 +194,7 @@ def run_ours(args):
                 s = p["solver"]
                 K = s.assemble(fs.E_mod, fs.A, fs.I)
                 r = s.load_case(K, p["kd_d"], p["kv_d"], react_dofs=p["react"], rtol=RTOL, precond=args.precond,
-                                gather_U=False)
+                                gather_U=False, maxit=MAXIT)
                 info[c] = {"iterations": r["iterations"], "relres": r["relres"], "total_force": r["total_force"],
                            "nnz_local": K.nnz}
                 p["last"] = (K, r)
@@ -269,7 +270,7 @@ def run_ours(args):
                 force, iters, rel, nnz = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
                 check(ctx.h, lib.myc_load_case_host(
                     ctx.h, ptr(h["coords"]), ptr(h["n1"]), ptr(h["n2"]), None, len(h["n1"]), len(h["coords"]),
-                    float(fs.E_mod), fs.A, fs.I, ptr(p["kd"]), ptr(p["kv"]), len(p["kd"]), 1e-12, pc, RTOL, 2_000_000,
+                    float(fs.E_mod), fs.A, fs.I, ptr(p["kd"]), ptr(p["kv"]), len(p["kd"]), 1e-12, pc, RTOL, MAXIT,
                     ptr(p["react"]), len(p["react"]), ptr(h["U"]), C.byref(force), C.byref(iters), C.byref(rel),
                     C.byref(nnz), None, None))
         api = "myc_load_case_host (C-ABI, host buffers)"
@@ -295,7 +296,8 @@ def run_ours(args):
                 kd = h["kd"].to(dev, non_blocking=True)
                 kv = h["kv"].to(dev, non_blocking=True)
                 K = s.assemble(fs.E_mod, fs.A, fs.I)
-                r = s.load_case(K, kd, kv, react_dofs=p["react"], rtol=RTOL, precond=args.precond, gather_U=False)
+                r = s.load_case(K, kd, kv, react_dofs=p["react"], rtol=RTOL, precond=args.precond, gather_U=False,
+                                maxit=MAXIT)
                 lo = K.row_offset
                 h["U"].copy_(r["U"][lo:lo + K.n_rows], non_blocking=True)
                 torch.cuda.synchronize()

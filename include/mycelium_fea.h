@@ -188,16 +188,19 @@ int myc_strain_update(myc_ctx* ctx, const double* d_coords, const int32_t* d_n1,
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The matrix is row-partitioned by contiguous node ranges
  * (PETSc MPIAIJ row blocks: MatSetSizes(..PETSC_DECIDE..), src/fea_petsc_parallel.cpp:236).
- * myc_dist_init loads NCCL (h_nccl_path: path of libnccl.so.2, or NULL for the default
- * search path), and joins the communicator described by the 128-byte unique id created by
+ * myc_dist_init loads NCCL (h_nccl_path: path of libnccl.so.2, or NULL for the default search
+ * path) and joins the communicator described by the 128-byte unique id created by
  * myc_dist_unique_id on rank 0 and distributed by the host (torch.distributed broadcast).
- * h_node_offsets: world+1 node offsets of the partition.  h_need_lo/h_need_hi: for THIS rank,
- * per peer q, the half-open global node range of q's nodes whose values this rank reads
- * (lo==hi: nothing); the library all-gathers the table so that every rank knows what to send.
+ * myc_dist_set_plan installs the partition of the mesh about to be solved (may be called any
+ * number of times, no communication): h_node_offsets = world+1 node offsets; for THIS rank and
+ * each peer q, [need_lo,need_hi) is the half-open global node range of q's nodes whose values
+ * this rank reads and [give_lo,give_hi) the range of this rank's nodes that q reads (the
+ * transpose, exchanged by the host); lo == hi means nothing.
  */
 int myc_dist_unique_id(const char* h_nccl_path, uint8_t* h_out_id128);
-int myc_dist_init(myc_ctx* ctx, const char* h_nccl_path, const uint8_t* h_id128, int rank, int world,
-                  const int64_t* h_node_offsets, const int64_t* h_need_lo, const int64_t* h_need_hi);
+int myc_dist_init(myc_ctx* ctx, const char* h_nccl_path, const uint8_t* h_id128, int rank, int world);
+int myc_dist_set_plan(myc_ctx* ctx, const int64_t* h_node_offsets, const int64_t* h_need_lo,
+                      const int64_t* h_need_hi, const int64_t* h_give_lo, const int64_t* h_give_hi);
 /* Refresh the halo entries of a global-length vector from their owners (VecScatter of
  * MatMult, src/fea_petsc_parallel.cpp:402).  Collective. */
 int myc_halo_exchange(myc_ctx* ctx, double* d_x_global, void* stream);

@@ -74,7 +74,8 @@ SIGNATURES = {
     "myc_gather_sum": [_p, _p, _p, _i64, _pf64, _p],
     "myc_strain_update": [_p, _p, _p, _p, _i64, _p, _f64, _f64, _p, _p, _pi64, _p],
     "myc_dist_unique_id": [C.c_char_p, _p],
-    "myc_dist_init": [_p, C.c_char_p, _p, _int, _int, _p, _p, _p],
+    "myc_dist_init": [_p, C.c_char_p, _p, _int, _int],
+    "myc_dist_set_plan": [_p, _p, _p, _p, _p, _p],
     "myc_halo_exchange": [_p, _p, _p],
     "myc_allreduce_sum": [_p, _pf64, _int, _p],
     "myc_allgather_owned": [_p, _p, _p],

@@ -90,11 +90,9 @@ extern "C" int myc_dist_unique_id(const char* h_nccl_path, uint8_t* h_out_id128)
 }
 
 extern "C" int myc_dist_init(myc_ctx* ctx, const char* h_nccl_path, const uint8_t* h_id128, int rank,
-                             int world, const int64_t* h_node_offsets, const int64_t* h_need_lo,
-                             const int64_t* h_need_hi) {
+                             int world) {
   if (!ctx) return MYC_ERR_BAD_ARG;
-  if (!h_id128 || world < 1 || rank < 0 || rank >= world || !h_node_offsets || !h_need_lo || !h_need_hi)
-    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "dist_init: bad argument");
+  if (!h_id128 || world < 1 || rank < 0 || rank >= world) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "dist_init: bad argument");
   if (ctx->comm) MYC_FAIL(ctx, MYC_ERR_STATE, "dist_init: context already has a communicator");
   MYC_CUDA(ctx, cudaSetDevice(ctx->device));
   ctx->nccl = load_nccl(h_nccl_path);
@@ -106,36 +104,37 @@ extern "C" int myc_dist_init(myc_ctx* ctx, const char* h_nccl_path, const uint8_
   ctx->comm = comm;
   ctx->rank = rank;
   ctx->world = world;
-  ctx->node_offsets = (int64_t*)malloc(sizeof(int64_t) * (world + 1));
-  memcpy(ctx->node_offsets, h_node_offsets, sizeof(int64_t) * (world + 1));
+  ctx->node_offsets = (int64_t*)calloc(world + 1, sizeof(int64_t));
   ctx->recv_from = (PeerRange*)calloc(world, sizeof(PeerRange));
   ctx->send_to = (PeerRange*)calloc(world, sizeof(PeerRange));
-  // all-gather the (world x 2*world) table of needed node ranges
-  const size_t row = 2 * (size_t)world;
-  int64_t* h_tab = (int64_t*)malloc(sizeof(int64_t) * row * world);
-  int64_t* d_tab = nullptr;
-  MYC_CUDA(ctx, cudaMalloc(&d_tab, sizeof(int64_t) * row * world));
+  return MYC_OK;
+}
+
+extern "C" int myc_dist_set_plan(myc_ctx* ctx, const int64_t* h_node_offsets, const int64_t* h_need_lo,
+                                 const int64_t* h_need_hi, const int64_t* h_give_lo, const int64_t* h_give_hi) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  if (!h_node_offsets || !h_need_lo || !h_need_hi || !h_give_lo || !h_give_hi)
+    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "dist_set_plan: null pointer");
+  if (ctx->world <= 1) return MYC_OK;
+  if (!ctx->comm) MYC_FAIL(ctx, MYC_ERR_STATE, "dist_set_plan: call myc_dist_init first");
+  const int world = ctx->world, rank = ctx->rank;
+  for (int q = 0; q <= world; ++q)
+    if (h_node_offsets[q] < 0 || (q > 0 && h_node_offsets[q] < h_node_offsets[q - 1]))
+      MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "dist_set_plan: node offsets must be non-decreasing");
+  memcpy(ctx->node_offsets, h_node_offsets, sizeof(int64_t) * (world + 1));
   for (int q = 0; q < world; ++q) {
-    int64_t lo = h_need_lo[q], hi = h_need_hi[q];
-    if (q == rank || hi <= lo) lo = hi = 0;
-    if (lo < h_node_offsets[q] || hi > h_node_offsets[q + 1]) {
-      if (hi > lo) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "dist_init: needed range [%lld,%lld) is not owned by rank %d", (long long)lo, (long long)hi, q);
-    }
-    h_tab[rank * row + 2 * q] = lo;
-    h_tab[rank * row + 2 * q + 1] = hi;
-    ctx->recv_from[q].lo = 3 * lo;
-    ctx->recv_from[q].hi = 3 * hi;
+    int64_t nlo = h_need_lo[q], nhi = h_need_hi[q], glo = h_give_lo[q], ghi = h_give_hi[q];
+    if (q == rank || nhi <= nlo) nlo = nhi = 0;
+    if (q == rank || ghi <= glo) glo = ghi = 0;
+    if (nhi > nlo && (nlo < h_node_offsets[q] || nhi > h_node_offsets[q + 1]))
+      MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "dist_set_plan: needed range [%lld,%lld) is not owned by rank %d", (long long)nlo, (long long)nhi, q);
+    if (ghi > glo && (glo < h_node_offsets[rank] || ghi > h_node_offsets[rank + 1]))
+      MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "dist_set_plan: given range [%lld,%lld) is not owned by this rank", (long long)glo, (long long)ghi);
+    ctx->recv_from[q].lo = 3 * nlo;
+    ctx->recv_from[q].hi = 3 * nhi;
+    ctx->send_to[q].lo = 3 * glo;
+    ctx->send_to[q].hi = 3 * ghi;
   }
-  MYC_CUDA(ctx, cudaMemcpy(d_tab + rank * row, h_tab + rank * row, sizeof(int64_t) * row, cudaMemcpyHostToDevice));
-  MYC_NCCL(ctx, ctx->nccl->AllGather(d_tab + rank * row, d_tab, row, MYC_NCCL_INT64, comm, 0));
-  MYC_CUDA(ctx, cudaStreamSynchronize(0));
-  MYC_CUDA(ctx, cudaMemcpy(h_tab, d_tab, sizeof(int64_t) * row * world, cudaMemcpyDeviceToHost));
-  for (int q = 0; q < world; ++q) {   // what rank q needs from me
-    ctx->send_to[q].lo = 3 * h_tab[q * row + 2 * rank];
-    ctx->send_to[q].hi = 3 * h_tab[q * row + 2 * rank + 1];
-  }
-  cudaFree(d_tab);
-  free(h_tab);
   return MYC_OK;
 }
 

@@ -155,26 +155,36 @@ class DistributedSolver:
             t = torch.from_numpy(uid).to(self.ctx.device)
             dist.broadcast(t, 0)
             uid = t.cpu().numpy()
-            p = self.plan
-            check(self.ctx.h, lib.myc_dist_init(
-                self.ctx.h, path, uid.ctypes.data_as(C.c_void_p), self.rank, self.world,
-                p.offsets.ctypes.data_as(C.c_void_p), p.need_lo.ctypes.data_as(C.c_void_p),
-                p.need_hi.ctypes.data_as(C.c_void_p)))
+            check(self.ctx.h, lib.myc_dist_init(self.ctx.h, path, uid.ctypes.data_as(C.c_void_p), self.rank,
+                                                self.world))
             self.ctx.rank, self.ctx.world = self.rank, self.world
-            self.ctx.node_offsets = p.offsets
+        self._install_plan()
+
+    def _install_plan(self):
+        """Make this solver's partition the one the C library's collectives use (several solvers,
+        e.g. one per load-case mesh, may share the device context)."""
+        from ._lib import lib, check
+        if self.world == 1:
+            return
+        p = self.plan
+        keep = [np.ascontiguousarray(a, dtype=np.int64) for a in (p.offsets, p.need_lo, p.need_hi, p.give_lo, p.give_hi)]
+        check(self.ctx.h, lib.myc_dist_set_plan(self.ctx.h, *[a.ctypes.data_as(C.c_void_p) for a in keep]))
+        self.ctx.node_offsets = p.offsets
 
     def assemble(self, E, A, I):
         from . import device as dv
+        self._install_plan()
         return dv.assemble(self.ctx, self.mesh, E, A, I, node_range=(self.plan.node_begin, self.plan.node_end))
 
     def load_case(self, K, known_dofs, known_vals, react_dofs=None, rtol=1e-10, precond="jacobi",
-                  maxit=2_000_000, reg=1e-12, gather_U=True):
+                  maxit=500_000, reg=1e-12, gather_U=True):
         """Returns dict(U (global, on every rank if gather_U), iterations, relres, total_force)."""
         import torch
         from . import device as dv
         from ._lib import lib, check
         ctx = self.ctx
         dev = ctx.device
+        self._install_plan()
         td = lambda a, dt: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
         kd, kv = td(known_dofs, np.int64), td(known_vals, np.float64)
         sysd = dv.apply_dirichlet(ctx, K, kd, kv, reg, block3=(precond == "block3"))

@@ -48,7 +48,7 @@ REGULARISATION = 1e-12          # fea_solver.py:125
 
 # solver knobs (not in the reference, which uses a direct solve)
 PCG_RTOL = 1e-10
-PCG_MAXIT = 2_000_000
+PCG_MAXIT = 500_000
 PCG_PRECOND = "jacobi"          # or "block3"
 
 
