@@ -103,6 +103,7 @@ __global__ void pcg_set_tol_kernel(PcgScalars* sc, double rtol, double atol) {
   const double t = fmax(rtol * rtol * sc->bb, atol * atol);
   sc->tol2 = t;
   sc->red[1] = sc->out[0];
+  sc->rr_final = sc->out[0];
   if (sc->out[0] <= t) { sc->done = 1; sc->iters = 0; }
 }
 
@@ -171,6 +172,7 @@ pcg_direction_kernel(int64_t n_rows, int64_t row_offset, const double* __restric
   if (sc->red[1] <= sc->tol2 || sc->breakdown) {   // uniform across the grid
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       sc->iters = iter_done;
+      sc->rr_final = sc->red[1];
       __threadfence();
       sc->done = 1;
     }
@@ -353,14 +355,15 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
     }
     ctx->prof_launches += live;
   }
-  const double relres = last.bb > 0.0 ? sqrt(last.red[1] / last.bb) : 0.0;
+  const double rr_last = last.done ? last.rr_final : last.red[1];
+  const double relres = last.bb > 0.0 ? sqrt(rr_last / last.bb) : 0.0;
   if (h_out_iters) *h_out_iters = last.done ? (int64_t)last.iters : it;
   if (h_out_relres) *h_out_relres = relres;
   if (last.breakdown || !(relres == relres))
     MYC_FAIL(ctx, MYC_ERR_BREAKDOWN, "pcg_solve: breakdown (p.Ap = %g, r.r = %g) after %lld iterations",
-             last.pAp, last.red[1], (long long)(last.done ? last.iters : it));
+             last.pAp, rr_last, (long long)(last.done ? last.iters : it));
   if (!last.done) {
-    if (last.red[1] <= last.tol2) return MYC_OK;     // converged exactly at maxit
+    if (rr_last <= last.tol2) return MYC_OK;         // converged exactly at maxit
     MYC_FAIL(ctx, MYC_ERR_NOT_CONVERGED, "pcg_solve: %lld iterations, ||r||/||b|| = %.3e > rtol", (long long)it, relres);
   }
   return MYC_OK;

@@ -121,6 +121,7 @@ struct PcgScalars {
   double bb;        // b.b
   double tol2;      // convergence threshold on r.r
   double out[4];    // generic outputs of one-shot reductions
+  double rr_final;  // r.r at the moment `done` was set (later all-reduces keep summing red[])
   int done;         // set once r.r <= tol2
   int breakdown;    // p.Ap <= 0 or not finite
   long long iters;  // iterations performed when `done` was set
