@@ -28,6 +28,8 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
   {
     const char* e = getenv("MYC_FORCE_PLAIN_SPMV");
     ctx->force_plain_spmv = e && e[0] == '1';
+    const char* f = getenv("MYC_NO_FUSED_PCG");
+    ctx->no_fused_pcg = f && f[0] == '1';
   }
   e = cudaSetDevice(device_ordinal);
   cudaDeviceProp prop;

@@ -27,6 +27,7 @@ struct myc_ctx {
   char err[512] = {0};
   int64_t launches = 0;
   bool force_plain_spmv = false;   // MYC_FORCE_PLAIN_SPMV=1: use the non-TMA CSR-stream kernel
+  bool no_fused_pcg = false;       // MYC_NO_FUSED_PCG=1: always use the multi-kernel PCG
 
   // ---- scratch arenas (grown on demand, never shrunk)
   DevBuf scan_tmp;              // block sums of the exclusive scan (all levels)

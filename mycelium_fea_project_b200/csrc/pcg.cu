@@ -19,6 +19,9 @@
 
 int myc_dist_allreduce_dev(myc_ctx* ctx, double* d_buf, int n, cudaStream_t st);   // dist.cu
 int myc_dist_halo(myc_ctx* ctx, double* d_x_global, cudaStream_t st);              // dist.cu
+int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, const int32_t* d_row_ptr, const int32_t* d_col_idx,
+                      const double* d_val, const double* d_dinv, double reg, int64_t maxit, double* d_x,
+                      cudaStream_t st, int* handled);                               // pcg_fused.cu
 
 namespace {
 
@@ -283,6 +286,39 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   MYC_CUDA(ctx, cudaMemcpyAsync(&sc->bb, &sc->out[1], sizeof(double), cudaMemcpyDeviceToDevice, st));
   pcg_set_tol_kernel<<<1, 1, 0, st>>>(sc, rtol, atol);
   MYC_LAUNCHED(ctx);
+  // ---- single-GPU Jacobi: the whole iteration loop is one persistent cooperative kernel
+  if (!block3 && !dist) {
+    int handled = 0;
+    if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
+    MYC_TRY(myc_pcg_fused_try(ctx, n_rows, d_row_ptr, d_col_idx, d_val, d_dinv, reg, maxit, d_x, st, &handled));
+    if (handled) {
+      if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
+      MYC_CUDA(ctx, cudaMemcpyAsync(h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+      MYC_CUDA(ctx, cudaStreamSynchronize(st));
+      const PcgScalars fin = *h_sc;
+      const double rel = fin.bb > 0.0 ? sqrt(fin.rr_final / fin.bb) : 0.0;
+      if (ctx->prof_on) {
+        float ms = 0.f;
+        int32_t h_nnz = 0;
+        MYC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[0], ctx->prof_ev[1]));
+        MYC_CUDA(ctx, cudaMemcpy(&h_nnz, d_row_ptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        ctx->prof_ms += ms;
+        ctx->prof_samples += 1;
+        ctx->prof_launches += 1;
+        ctx->prof_bytes += ((double)fin.iters + 1.0) * (12.0 * h_nnz + 20.0 * (double)n_rows) +
+                           (double)fin.iters * 96.0 * (double)n_rows;
+      }
+      if (h_out_iters) *h_out_iters = (int64_t)fin.iters;
+      if (h_out_relres) *h_out_relres = rel;
+      if (fin.breakdown || !(rel == rel))
+        MYC_FAIL(ctx, MYC_ERR_BREAKDOWN, "pcg_solve (fused): breakdown after %lld iterations, r.r = %g",
+                 (long long)fin.iters, fin.rr_final);
+      if (!fin.done)
+        MYC_FAIL(ctx, MYC_ERR_NOT_CONVERGED, "pcg_solve: %lld iterations, ||r||/||b|| = %.3e > rtol",
+                 (long long)fin.iters, rel);
+      return MYC_OK;
+    }
+  }
   if (block3)
     pcg_init_kernel<true><<<vgrid, VEC_THREADS, 0, st>>>(n_rows, row_offset, r, d_dinv, d_binv, pg, zv, partials, sc);
   else

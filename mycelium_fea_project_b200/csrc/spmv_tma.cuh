@@ -74,44 +74,59 @@ __device__ __forceinline__ void tm_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void tm_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <class Epi>
-__global__ void __launch_bounds__(TM_THREADS, TM_BLOCKS_PER_SM)
-myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_t* __restrict__ ci,
-                    const double* __restrict__ v, const double* __restrict__ x, Epi epi, double* partials,
-                    unsigned* counter, double* out, const int* done) {
-  extern __shared__ __align__(128) unsigned char tm_smem[];
-  __shared__ double s_warp[TM_THREADS / 32];
-  if (done && *done) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* s_val = reinterpret_cast<double*>(tm_smem) + (size_t)warp * TM_STAGES * TM_CAP;
-  int32_t* s_col = reinterpret_cast<int32_t*>(tm_smem + (size_t)TM_WARPS * TM_STAGES * TM_CAP * sizeof(double)) +
-                   (size_t)warp * TM_STAGES * TM_CAP;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tm_smem + TM_WARPS * TM_SMEM_PER_WARP) + warp * TM_STAGES;
+// Per-warp pipeline state.  It outlives one sweep over the matrix, so a persistent kernel (the
+// fused PCG, pcg_fused.cu) can keep the matrix stream running across solver iterations: at the
+// end of a sweep the first tile of the NEXT sweep is already requested (the matrix does not
+// change between iterations, only the gathered vector does).
+struct TmPipe {
+  double* s_val;
+  int32_t* s_col;
+  uint64_t* bars;
+  uint64_t l2_stream;
+  uint32_t phase_bits;
+  bool head_in_flight;     // tile 0 of the coming sweep has been issued into stage 0
+};
 
-  double acc[Epi::NACC == 0 ? 1 : Epi::NACC];
-#pragma unroll
-  for (int j = 0; j < (Epi::NACC == 0 ? 1 : Epi::NACC); ++j) acc[j] = 0.0;
-
-  // Tiles are dealt round-robin over all warps of the grid (tile = gw + j * n_warps): at any time
-  // the whole chip works inside one moving window of ~n_warps*32 rows, so the x entries gathered
-  // by neighbouring tiles are shared in L2/L1 instead of being spread over the whole vector.
-  const int64_t n_tiles = (n_rows + TM_ROWS - 1) / TM_ROWS;
-  const int64_t n_warps = (int64_t)gridDim.x * TM_WARPS;
-  const int64_t gw = (int64_t)blockIdx.x * TM_WARPS + warp;
-  const int64_t t_count = gw < n_tiles ? (n_tiles - gw + n_warps - 1) / n_warps : 0;
-  const int32_t nnz_total = rp[n_rows];
-  const int32_t nnz4 = nnz_total & ~3;
-  uint64_t l2_stream;   // the matrix is read once per SpMV: evict-first, keep L2 for x
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
-
+__device__ __forceinline__ void tm_pipe_init(TmPipe& pp, unsigned char* smem_base, int warps_per_block, int warp,
+                                             int lane) {
+  pp.s_val = reinterpret_cast<double*>(smem_base) + (size_t)warp * TM_STAGES * TM_CAP;
+  pp.s_col = reinterpret_cast<int32_t*>(smem_base + (size_t)warps_per_block * TM_STAGES * TM_CAP * sizeof(double)) +
+             (size_t)warp * TM_STAGES * TM_CAP;
+  pp.bars = reinterpret_cast<uint64_t*>(smem_base + (size_t)warps_per_block * TM_SMEM_PER_WARP) + warp * TM_STAGES;
+  pp.phase_bits = 0;
+  pp.head_in_flight = false;
+  // the matrix is read once per sweep: evict-first, keep L2 for the gathered vector
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pp.l2_stream));
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < TM_STAGES; ++s) tm_mbar_init(&bars[s], 1);
+    for (int s = 0; s < TM_STAGES; ++s) tm_mbar_init(&pp.bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+}
 
-  // row pointers of tile t: lane l holds rp[32t + l] and rp[32t + l + 1] (clamped)
+// One sweep of warp `gw` (of n_warps) over its tiles: y-rows are handed to epi.row(row, sum, acc).
+// COHERENT_X: the gathered vector is written by other SMs between sweeps of the same kernel, so
+// it must not be read through the non-coherent (ld.global.nc) path.
+// PREFETCH_NEXT: request tile 0 of the next sweep before returning.
+template <class Epi, bool COHERENT_X, bool PREFETCH_NEXT>
+__device__ __forceinline__ void tm_warp_sweep(TmPipe& pp, int64_t n_rows, const int32_t* __restrict__ rp,
+                                              const int32_t* __restrict__ ci, const double* __restrict__ v,
+                                              const double* x, const Epi& epi,
+                                              double (&acc)[Epi::NACC == 0 ? 1 : Epi::NACC], int64_t gw,
+                                              int64_t n_warps, int lane, int32_t nnz_total) {
+  static_assert(TM_STAGES == 2, "the sweep is written for a 2-stage ring");
+  // Tiles are dealt round-robin over all warps of the grid (tile = gw + j * n_warps): at any time
+  // the whole chip works inside one moving window of ~n_warps*TM_ROWS rows, so the x entries gathered
+  // by neighbouring tiles are shared in L2/L1 instead of being spread over the whole vector.
+  const int64_t n_tiles = (n_rows + TM_ROWS - 1) / TM_ROWS;
+  const int64_t t_count = gw < n_tiles ? (n_tiles - gw + n_warps - 1) / n_warps : 0;
+  const int32_t nnz4 = nnz_total & ~3;
+  double* const s_val = pp.s_val;
+  int32_t* const s_col = pp.s_col;
+  uint64_t* const bars = pp.bars;
+
+  // row pointers of tile t: lane l holds rp[T*t + l] and rp[T*t + l + 1] (clamped)
   auto load_rp = [&](int64_t t, int32_t& lo_l, int32_t& hi_l) {
     const int64_t r = t * TM_ROWS + (lane < TM_ROWS ? lane : TM_ROWS - 1);
     lo_l = rp[r < n_rows ? r : n_rows];
@@ -125,21 +140,25 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
     const int32_t n = a1 - a0;
     if (hi > lo && hi - a0 <= TM_CAP && n > 0) {
       tm_mbar_expect_tx(&bars[s], (uint32_t)n * 12u);
-      tm_bulk_load(s_val + (size_t)s * TM_CAP, v + a0, (uint32_t)n * 8u, &bars[s], l2_stream);
-      tm_bulk_load(s_col + (size_t)s * TM_CAP, ci + a0, (uint32_t)n * 4u, &bars[s], l2_stream);
+      tm_bulk_load(s_val + (size_t)s * TM_CAP, v + a0, (uint32_t)n * 8u, &bars[s], pp.l2_stream);
+      tm_bulk_load(s_col + (size_t)s * TM_CAP, ci + a0, (uint32_t)n * 4u, &bars[s], pp.l2_stream);
     }
   };
 
   // Register pipeline of row pointers: tile j (cur), j+1 (nxt); tile j+2 is requested at the top
   // of iteration j, so no global-load latency sits on the critical path.
   int32_t cur_lo = 0, cur_hi = 0, nxt_lo = 0, nxt_hi = 0;
+  int32_t head_lo = 0, head_hi = 0;          // tile 0 again, for PREFETCH_NEXT
   if (t_count > 0) {
     load_rp(gw, cur_lo, cur_hi);
     if (t_count > 1) load_rp(gw + n_warps, nxt_lo, nxt_hi);
-    const int32_t lo = __shfl_sync(0xffffffffu, cur_lo, 0), hi = __shfl_sync(0xffffffffu, cur_hi, TM_ROWS - 1);
-    if (lane == 0) issue(0, lo, hi);
+    head_lo = __shfl_sync(0xffffffffu, cur_lo, 0);
+    head_hi = __shfl_sync(0xffffffffu, cur_hi, TM_ROWS - 1);
+    // stage of tile j is (j + base) % 2 where base makes tile 0 land in the stage the previous
+    // sweep left free; with the head already in flight it sits in stage `head_stage`.
+    if (!pp.head_in_flight && lane == 0) issue(0, head_lo, head_hi);
   }
-  uint32_t phase_bits = 0;
+  // when the previous sweep prefetched the head, it did so into stage 0 as well (see below)
 
   for (int64_t j = 0; j < t_count; ++j) {
     const int s = (int)(j % TM_STAGES);
@@ -165,8 +184,8 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
         int32_t a1 = (hi + 3) & ~3;
         if (a1 > nnz4) a1 = nnz4;
         if (a1 > a0) {
-          tm_mbar_wait(&bars[s], (phase_bits >> s) & 1u);
-          phase_bits ^= (1u << s);
+          tm_mbar_wait(&bars[s], (pp.phase_bits >> s) & 1u);
+          pp.phase_bits ^= (1u << s);
         }
         const int first = lo - a0, last = hi - a0, staged = a1 - a0;
         if (staged < last) {                      // ragged end of the whole array (< 4 elements)
@@ -184,7 +203,10 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
           c[u] = k < last ? sc[k] : -1;
         }
 #pragma unroll
-        for (int u = 0; u < TM_MAXIT; ++u) xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+        for (int u = 0; u < TM_MAXIT; ++u) {
+          if constexpr (COHERENT_X) xv[u] = c[u] >= 0 ? x[c[u]] : 0.0;
+          else xv[u] = c[u] >= 0 ? __ldg(x + c[u]) : 0.0;
+        }
 #pragma unroll
         for (int u = 0; u < TM_MAXIT; ++u) {
           const int k = first + lane + 32 * u;
@@ -206,14 +228,44 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
         __syncwarp();
       } else if (row_ok) {
         // oversize tile: lane-per-row straight from global memory (left-to-right, deterministic)
-        for (int32_t q = my_lo; q < my_hi; ++q) sum += v[q] * __ldg(x + ci[q]);
+        for (int32_t q = my_lo; q < my_hi; ++q) sum += v[q] * (COHERENT_X ? x[ci[q]] : __ldg(x + ci[q]));
       }
     }
     if (row_ok) epi.row(r0 + lane, sum, acc);
     cur_lo = nxt_lo; cur_hi = nxt_hi;
     nxt_lo = nn_lo; nxt_hi = nn_hi;
   }
+  // Stage bookkeeping across sweeps: tile j uses stage j % 2, so a sweep with an odd tile count
+  // would leave the ring "rotated".  To keep "tile 0 -> stage 0" true for every sweep, a warp with
+  // an odd t_count simply lets the next head overwrite stage 0, which its last tile (index
+  // t_count-1, even -> stage 0) has just released; with an even t_count stage 0 was released one
+  // tile earlier.  Either way stage 0 is free here.
+  if constexpr (PREFETCH_NEXT) {
+    if (t_count > 0) {
+      if (lane == 0) issue(0, head_lo, head_hi);
+      pp.head_in_flight = true;
+    }
+  } else {
+    pp.head_in_flight = false;
+  }
+}
 
+template <class Epi>
+__global__ void __launch_bounds__(TM_THREADS, TM_BLOCKS_PER_SM)
+myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_t* __restrict__ ci,
+                    const double* __restrict__ v, const double* __restrict__ x, Epi epi, double* partials,
+                    unsigned* counter, double* out, const int* done) {
+  extern __shared__ __align__(128) unsigned char tm_smem[];
+  __shared__ double s_warp[TM_THREADS / 32];
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TmPipe pp;
+  tm_pipe_init(pp, tm_smem, TM_WARPS, warp, lane);
+  double acc[Epi::NACC == 0 ? 1 : Epi::NACC];
+#pragma unroll
+  for (int j = 0; j < (Epi::NACC == 0 ? 1 : Epi::NACC); ++j) acc[j] = 0.0;
+  tm_warp_sweep<Epi, false, false>(pp, n_rows, rp, ci, v, x, epi, acc, (int64_t)blockIdx.x * TM_WARPS + warp,
+                                   (int64_t)gridDim.x * TM_WARPS, lane, rp[n_rows]);
   if constexpr (Epi::NACC > 0) {
 #pragma unroll
     for (int j = 0; j < Epi::NACC; ++j) acc[j] = myc_block_reduce(acc[j], s_warp);

@@ -289,6 +289,32 @@ def test_solve_512_vs_direct(monkeypatch):
         assert tr <= 1e-10
 
 
+def test_fused_pcg_matches_multikernel_pcg(ctx, monkeypatch):
+    """The persistent single-kernel PCG (Chronopoulos-Gear recurrence) and the three-kernel PCG
+    (Hestenes-Stiefel) must agree on U to solver tolerance and need about as many iterations."""
+    coords, n1, n2 = synth_network(128)
+    mesh = dv.DeviceMesh.from_host(coords, n1, n2)
+    K = dv.assemble(ctx, mesh, fs.E_mod, fs.A, fs.I)
+    kd, kv = fs.build_bc(*fs.grip_nodes(coords, 0.5), 0.02, -0.02)
+    sysd = dv.apply_dirichlet(ctx, K, _dev(kd, np.int64), _dev(kv, np.float64))
+    x1, it1, rel1 = dv.pcg(ctx, K, sysd, rtol=1e-12)
+    tr1 = dv.true_residual(ctx, K, sysd, x1)
+    monkeypatch.setenv("MYC_NO_FUSED_PCG", "1")
+    ctx2 = dv.Context(0)
+    try:
+        x2, it2, rel2 = dv.pcg(ctx2, K, sysd, rtol=1e-12)
+        tr2 = dv.true_residual(ctx2, K, sysd, x2)
+    finally:
+        ctx2.close()
+    print(f"fused: it={it1} rel={rel1:.2e} true={tr1:.2e} | multi-kernel: it={it2} rel={rel2:.2e} true={tr2:.2e}")
+    a, b = x1.cpu().numpy(), x2.cpu().numpy()
+    assert np.linalg.norm(a - b) <= 1e-9 * np.linalg.norm(b)
+    assert abs(it1 - it2) <= 0.05 * it2 + 5
+    assert tr1 <= 5e-12 and tr2 <= 5e-12
+    x3, it3, _ = dv.pcg(ctx, K, sysd, rtol=1e-12)          # reproducible bit for bit
+    assert it3 == it1 and torch.equal(x3, x1)
+
+
 def test_pcg_zero_rhs_and_all_known(ctx):
     coords, n1, n2 = synth_network(16)
     mesh = dv.DeviceMesh.from_host(coords, n1, n2)

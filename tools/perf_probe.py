@@ -58,6 +58,7 @@ def main():
             kd, kv = fs.build_bc(hi, lo, 0.02, -0.02, 1)
             sysd = dv.apply_dirichlet(ctx, K, torch.from_numpy(kd).cuda(), torch.from_numpy(kv).cuda(),
                                       block3=(a.precond == "block3"))
+            dv.pcg(ctx, K, sysd, precond=a.precond, rtol=a.rtol, maxit=20, raise_on_maxit=False)   # warm-up
             torch.cuda.synchronize()
             t0 = time.time()
             xs, it, rel = dv.pcg(ctx, K, sysd, precond=a.precond, rtol=a.rtol, maxit=a.maxit, raise_on_maxit=False)
