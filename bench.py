@@ -341,11 +341,15 @@ def run_ours(args):
     roof = None
     if spmv_n:
         ach = spmv_bytes / (spmv_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "myc_spmv_kernel<EpiCgAp> (Ap = K p + reg p, fused p.Ap)",
+        fused = world == 1 and args.precond == "jacobi" and os.environ.get("MYC_NO_FUSED_PCG") != "1"
+        kname = ("pcg_fused_kernel (one persistent launch per solve: TMA SpMV sweep + fused dots + vector "
+                 "recurrences per iteration; bytes = (its+1)*(12 nnz + 20 n) + its*96 n)") if fused else \
+            "myc_spmv_tma_kernel<EpiCgAp> (Ap = K p + reg p, fused p.Ap; every 32nd launch sampled)"
+        roof = {"bound": "hbm", "kernel": kname,
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src, "avg_launch_us": spmv_ms / spmv_n * 1e3, "launches_sampled": spmv_n,
                 "algorithmic_bytes_per_launch": spmv_bytes / spmv_n,
-                "share_of_step": (prof[3] * spmv_ms / spmv_n) / (ms_total) if ms_total else None,
+                "share_of_step": (spmv_ms / ms_total if fused else (prof[3] * spmv_ms / spmv_n) / ms_total) if ms_total else None,
                 "note": "per-rank operator; L2-resident at grid 512, so frac may exceed 1 -- see roofline_hbm"}
 
     line = {

@@ -49,8 +49,10 @@ struct EpiRhs {   // b = -(K u_bc) on free rows, 0 on known rows
   static constexpr int NACC = 0;
   double* b;
   const double* dinv;
-  __device__ __forceinline__ void row(int64_t r, double s, double (&)[1]) const {
-    b[r] = dinv[r] != 0.0 ? -s : 0.0;
+  struct Pre { double di; };
+  __device__ __forceinline__ Pre load(int64_t r) const { return Pre{dinv[r]}; }
+  __device__ __forceinline__ void row(int64_t r, double s, const Pre& pre, double (&)[1]) const {
+    b[r] = pre.di != 0.0 ? -s : 0.0;
   }
 };
 

@@ -13,6 +13,8 @@
 // grid), the host only polls a pinned copy every few dozen iterations, and once `done` is set
 // every queued kernel returns immediately.  On a distributed context the three scalars are
 // NCCL all-reduced in place and p's halo is refreshed before each SpMV.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "spmv.cuh"
 #include "spmv_tma.cuh"
@@ -34,8 +36,10 @@ struct EpiCgAp {   // Ap = K p + reg p ; acc0 = p.Ap
   const double* pg;
   int64_t row_offset;
   double reg;
-  __device__ __forceinline__ void row(int64_t r, double s, double (&acc)[1]) const {
-    const double pi = pg[row_offset + r];
+  struct Pre { double pi; };
+  __device__ __forceinline__ Pre load(int64_t r) const { return Pre{pg[row_offset + r]}; }
+  __device__ __forceinline__ void row(int64_t r, double s, const Pre& pre, double (&acc)[1]) const {
+    const double pi = pre.pi;
     const double y = s + reg * pi;
     Ap[r] = y;
     acc[0] += pi * y;
@@ -50,9 +54,11 @@ struct EpiResid {  // r = b - (K x + reg x) on free rows, 0 on known rows ; acc 
   const double* xg;
   int64_t row_offset;
   double reg;
-  __device__ __forceinline__ void row(int64_t r, double s, double (&acc)[2]) const {
-    const double bi = b[r];
-    const double res = dinv[r] != 0.0 ? bi - (s + reg * xg[row_offset + r]) : 0.0;
+  struct Pre { double bi, di, xi; };
+  __device__ __forceinline__ Pre load(int64_t r) const { return Pre{b[r], dinv[r], xg[row_offset + r]}; }
+  __device__ __forceinline__ void row(int64_t r, double s, const Pre& pre, double (&acc)[2]) const {
+    const double bi = pre.bi;
+    const double res = pre.di != 0.0 ? bi - (s + reg * pre.xi) : 0.0;
     r_out[r] = res;
     acc[0] += res * res;
     acc[1] += bi * bi;
@@ -296,6 +302,9 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       MYC_CUDA(ctx, cudaMemcpyAsync(h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
       MYC_CUDA(ctx, cudaStreamSynchronize(st));
       const PcgScalars fin = *h_sc;
+      if (getenv("MYC_FUSED_TIMING_PRINT"))
+        fprintf(stderr, "[fused] block0 ns/iter: sweep %.0f  barrier+reduce %.0f  vector %.0f  barrier %.0f  (iters %lld)\n",
+                fin.out[0], fin.out[1], fin.out[2], fin.out[3], (long long)fin.iters);
       const double rel = fin.bb > 0.0 ? sqrt(fin.rr_final / fin.bb) : 0.0;
       if (ctx->prof_on) {
         float ms = 0.f;

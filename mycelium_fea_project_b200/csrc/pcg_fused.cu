@@ -73,8 +73,10 @@ struct EpiFused {   // w = K u + reg u ; acc = {r.u, w.u, r.r}
   const double* u;
   const double* r;
   double reg;
-  __device__ __forceinline__ void row(int64_t i, double sum, double (&acc)[3]) const {
-    const double ui = u[i], ri = r[i];
+  struct Pre { double ui, ri; };
+  __device__ __forceinline__ Pre load(int64_t i) const { return Pre{u[i], r[i]}; }
+  __device__ __forceinline__ void row(int64_t i, double sum, const Pre& pre, double (&acc)[3]) const {
+    const double ui = pre.ui, ri = pre.ri;
     const double wi = sum + reg * ui;
     w[i] = wi;
     acc[0] += ri * ui;
@@ -82,6 +84,17 @@ struct EpiFused {   // w = K u + reg u ; acc = {r.u, w.u, r.r}
     acc[2] += ri * ri;
   }
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#ifdef MYC_FUSED_TIMING
+#define FT_MARK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long n_ = gtimer(); tacc[k] += n_ - tlast; tlast = n_; } } while (0)
+#else
+#define FT_MARK(k) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   extern __shared__ __align__(128) unsigned char fu_smem[];
@@ -108,6 +121,9 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   }
   grid_barrier(a.bar_counter, bar_target);
 
+#ifdef MYC_FUSED_TIMING
+  unsigned long long tacc[4] = {0, 0, 0, 0}, tlast = gtimer();
+#endif
   double gamma_old = 1.0, alpha_old = 1.0, rr = 0.0;
   long long it = 0;
   int status = 0;   // 1 converged, 2 breakdown, 0 maxit
@@ -116,6 +132,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     // ---- phase A: w = A u, partial dots
     double acc[3] = {0.0, 0.0, 0.0};
     tm_warp_sweep<EpiFused, true, true>(pp, n, a.rp, a.ci, a.v, a.u, epi, acc, gw, n_warps, lane, nnz_total);
+    FT_MARK(0);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       double t = acc[j];
@@ -142,6 +159,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
       }
     }
     __syncthreads();
+    FT_MARK(1);
     const double gamma = s_tot[0], delta = s_tot[1];
     rr = s_tot[2];
     if (!(rr > tol2)) { status = 1; break; }             // converged (x, r are consistent)
@@ -165,7 +183,9 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     gamma_old = gamma;
     alpha_old = alpha;
     ++it;
+    FT_MARK(2);
     grid_barrier(a.bar_counter, bar_target);
+    FT_MARK(3);
   }
   // drain the prefetched head tile so that no bulk copy is in flight when the block exits
   if (pp.head_in_flight) {
@@ -187,6 +207,9 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     a.sc->red[1] = rr;
     a.sc->done = (status == 1);
     a.sc->breakdown = (status == 2);
+#ifdef MYC_FUSED_TIMING
+    for (int k = 0; k < 4; ++k) a.sc->out[k] = (double)tacc[k] / (double)(it > 0 ? it : 1);   // ns per iteration
+#endif
   }
 }
 

@@ -56,7 +56,9 @@ __device__ __forceinline__ void myc_finalize_partials(double* partials, const do
 
 // Epi interface:
 //   static constexpr int NACC;                     number of fused partial sums
-//   __device__ void row(int64_t r, double sum, double (&acc)[NACC]) const;   r = local row
+//   struct Pre;  __device__ Pre load(int64_t r) const;     per-row operands, requested EARLY so
+//                                                          that their latency overlaps the tile
+//   __device__ void row(int64_t r, double sum, const Pre&, double (&acc)[NACC]) const;
 template <class Epi>
 __device__ __forceinline__ void myc_spmv_tiles(int64_t n_rows, const int32_t* __restrict__ rp,
                                                const int32_t* __restrict__ ci,
@@ -95,7 +97,7 @@ __device__ __forceinline__ void myc_spmv_tiles(int64_t n_rows, const int32_t* __
         double s = 0.0;
         const int e = s_rp[t + 1] - start;
         for (int j = s_rp[t] - start; j < e; ++j) s += s_prod[j];
-        epi.row(r0 + t, s, acc);
+        epi.row(r0 + t, s, epi.load(r0 + t), acc);
       }
     } else {
       // tile too dense for the staging buffer: one warp per row, lanes stride the row,
@@ -103,10 +105,10 @@ __device__ __forceinline__ void myc_spmv_tiles(int64_t n_rows, const int32_t* __
       const int lane = t & 31, warp = t >> 5;
       for (int r = warp; r < rows; r += SP_THREADS / 32) {
         double s = 0.0;
-        for (int32_t j = s_rp[r] + lane; j < s_rp[r + 1]; j += 32) s += v[j] * __ldg(x + ci[j]);
+        for (int32_t j = s_rp[r] + lane; j < s_rp[r + 1]; j += 32) s = __dadd_rn(s, __dmul_rn(v[j], __ldg(x + ci[j])));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) epi.row(r0 + r, s, acc);
+        if (lane == 0) epi.row(r0 + r, s, epi.load(r0 + r), acc);
       }
     }
     __syncthreads();
@@ -132,7 +134,9 @@ struct PcgScalars {
 struct EpiPlain {
   static constexpr int NACC = 0;
   double* y;
-  __device__ __forceinline__ void row(int64_t r, double s, double (&)[1]) const { y[r] = s; }
+  struct Pre {};
+  __device__ __forceinline__ Pre load(int64_t) const { return Pre{}; }
+  __device__ __forceinline__ void row(int64_t r, double s, const Pre&, double (&)[1]) const { y[r] = s; }
 };
 
 // Generic SpMV kernel: grid-stride over row tiles, optional fused reductions finalised by the

@@ -175,6 +175,8 @@ __device__ __forceinline__ void tm_warp_sweep(TmPipe& pp, int64_t n_rows, const 
     const int32_t hi = __shfl_sync(0xffffffffu, cur_hi, TM_ROWS - 1);
     const int32_t my_lo = cur_lo, my_hi = cur_hi;
     const bool row_ok = lane < TM_ROWS && (r0 + lane) < n_rows;
+    typename Epi::Pre pre{};
+    if (row_ok) pre = epi.load(r0 + lane);       // epilogue operands: in flight during the whole tile
     const int32_t a0 = lo & ~3;
     double sum = 0.0;
     if (hi > lo) {
@@ -228,10 +230,12 @@ __device__ __forceinline__ void tm_warp_sweep(TmPipe& pp, int64_t n_rows, const 
         __syncwarp();
       } else if (row_ok) {
         // oversize tile: lane-per-row straight from global memory (left-to-right, deterministic)
-        for (int32_t q = my_lo; q < my_hi; ++q) sum += v[q] * (COHERENT_X ? x[ci[q]] : __ldg(x + ci[q]));
+        // (product rounded before the add, like the staged path: identical bits on every path)
+        for (int32_t q = my_lo; q < my_hi; ++q)
+          sum = __dadd_rn(sum, __dmul_rn(v[q], COHERENT_X ? x[ci[q]] : __ldg(x + ci[q])));
       }
     }
-    if (row_ok) epi.row(r0 + lane, sum, acc);
+    if (row_ok) epi.row(r0 + lane, sum, pre, acc);
     cur_lo = nxt_lo; cur_hi = nxt_hi;
     nxt_lo = nn_lo; nxt_hi = nn_hi;
   }
