@@ -201,6 +201,18 @@ int myc_dist_unique_id(const char* h_nccl_path, uint8_t* h_out_id128);
 int myc_dist_init(myc_ctx* ctx, const char* h_nccl_path, const uint8_t* h_id128, int rank, int world);
 int myc_dist_set_plan(myc_ctx* ctx, const int64_t* h_node_offsets, const int64_t* h_need_lo,
                       const int64_t* h_need_hi, const int64_t* h_give_lo, const int64_t* h_give_hi);
+/* NVLink peer-memory path of myc_pcg_solve (Jacobi): every rank allocates one IPC-shareable buffer
+ * (gathered vector of n_cols_capacity doubles + flag/slot block), the host exchanges the 64-byte
+ * cudaIpcMemHandle_t of all ranks (h_handles = world x 64 bytes, rank order) and every rank opens
+ * its peers' buffers.  After that myc_pcg_solve runs as ONE persistent kernel per GPU: halo
+ * values are stored straight into the neighbours' buffers and dot products are exchanged through
+ * peer-written slots -- no NCCL call inside the iteration loop (csrc/pcg_fused.cu).  All three
+ * calls are collective; myc_dist_peer_disable makes every rank use the NCCL loop again (call it
+ * on all ranks if any rank failed to open a handle). */
+int myc_dist_peer_alloc(myc_ctx* ctx, int64_t n_cols_capacity, uint8_t* h_out_handle64);
+int myc_dist_peer_open(myc_ctx* ctx, const uint8_t* h_handles);
+int myc_dist_peer_disable(myc_ctx* ctx);
+
 /* Refresh the halo entries of a global-length vector from their owners (VecScatter of
  * MatMult, src/fea_petsc_parallel.cpp:402).  Collective. */
 int myc_halo_exchange(myc_ctx* ctx, double* d_x_global, void* stream);

@@ -76,6 +76,9 @@ SIGNATURES = {
     "myc_dist_unique_id": [C.c_char_p, _p],
     "myc_dist_init": [_p, C.c_char_p, _p, _int, _int],
     "myc_dist_set_plan": [_p, _p, _p, _p, _p, _p],
+    "myc_dist_peer_alloc": [_p, _i64, _p],
+    "myc_dist_peer_open": [_p, _p],
+    "myc_dist_peer_disable": [_p],
     "myc_halo_exchange": [_p, _p, _p],
     "myc_allreduce_sum": [_p, _pf64, _int, _p],
     "myc_allgather_owned": [_p, _p, _p],

@@ -8,6 +8,7 @@
 #include "../../include/mycelium_fea.h"
 
 #define MYC_SM_COUNT_FALLBACK 148
+#define MYC_MAX_WORLD 8          // ranks the NVLink peer-memory PCG supports (one HGX board)
 
 // Growable device scratch buffer owned by the context.
 struct DevBuf {
@@ -66,6 +67,13 @@ struct myc_ctx {
   int64_t* node_offsets = nullptr;   // world+1
   PeerRange* recv_from = nullptr;    // [world] DOF ranges this rank receives from peer q
   PeerRange* send_to = nullptr;      // [world] DOF ranges this rank sends to peer q
+  // NVLink peer memory of the fused multi-GPU PCG (pcg_fused.cu): one IPC-shared buffer per rank
+  // holding the gathered vector u (global length) followed by the PeerSync slots/flags
+  void* peer_own = nullptr;
+  void* peer_base[MYC_MAX_WORLD] = {nullptr};
+  int64_t peer_cap = 0;              // capacity of the u vector in doubles
+  bool peer_ok = false;
+  unsigned peer_epoch_red = 0, peer_epoch_halo = 0;
 };
 
 #define MYC_FAIL(ctx, code, ...)                                   \

@@ -138,7 +138,20 @@ extern "C" int myc_dist_set_plan(myc_ctx* ctx, const int64_t* h_node_offsets, co
   return MYC_OK;
 }
 
+extern "C" int myc_dist_peer_disable(myc_ctx* ctx) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  ctx->peer_ok = false;
+  return MYC_OK;
+}
+
 int myc_dist_destroy(myc_ctx* ctx) {
+  for (int q = 0; q < MYC_MAX_WORLD; ++q) {
+    if (ctx->peer_base[q] && q != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_base[q]);
+    ctx->peer_base[q] = nullptr;
+  }
+  if (ctx->peer_own) cudaFree(ctx->peer_own);
+  ctx->peer_own = nullptr;
+  ctx->peer_ok = false;
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy((myc_ncclComm_t)ctx->comm);
   ctx->comm = nullptr;
   free(ctx->node_offsets);

@@ -21,9 +21,10 @@
 
 int myc_dist_allreduce_dev(myc_ctx* ctx, double* d_buf, int n, cudaStream_t st);   // dist.cu
 int myc_dist_halo(myc_ctx* ctx, double* d_x_global, cudaStream_t st);              // dist.cu
-int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, const int32_t* d_row_ptr, const int32_t* d_col_idx,
-                      const double* d_val, const double* d_dinv, double reg, int64_t maxit, double* d_x,
-                      cudaStream_t st, int* handled);                               // pcg_fused.cu
+int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
+                      const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
+                      const double* d_dinv, double reg, int64_t maxit, double* d_x, cudaStream_t st,
+                      int* handled);                                                // pcg_fused.cu
 
 namespace {
 
@@ -292,16 +293,22 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   MYC_CUDA(ctx, cudaMemcpyAsync(&sc->bb, &sc->out[1], sizeof(double), cudaMemcpyDeviceToDevice, st));
   pcg_set_tol_kernel<<<1, 1, 0, st>>>(sc, rtol, atol);
   MYC_LAUNCHED(ctx);
-  // ---- single-GPU Jacobi: the whole iteration loop is one persistent cooperative kernel
-  if (!block3 && !dist) {
+  // ---- Jacobi: the whole iteration loop is one persistent cooperative kernel per GPU (NVLink peer
+  // memory between GPUs); falls through to the multi-kernel / NCCL loop when not applicable
+  if (!block3) {
     int handled = 0;
     if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
-    MYC_TRY(myc_pcg_fused_try(ctx, n_rows, d_row_ptr, d_col_idx, d_val, d_dinv, reg, maxit, d_x, st, &handled));
+    MYC_TRY(myc_pcg_fused_try(ctx, n_rows, n_cols_global, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv, reg, maxit,
+                              d_x, st, &handled));
     if (handled) {
       if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
       MYC_CUDA(ctx, cudaMemcpyAsync(h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
       MYC_CUDA(ctx, cudaStreamSynchronize(st));
       const PcgScalars fin = *h_sc;
+      if (dist) {
+        ctx->peer_epoch_red = (unsigned)fin.pAp;
+        ctx->peer_epoch_halo = (unsigned)fin.rz_old;
+      }
       if (getenv("MYC_FUSED_TIMING_PRINT"))
         fprintf(stderr, "[fused] block0 ns/iter: sweep %.0f  barrier+reduce %.0f  vector %.0f  barrier %.0f  (iters %lld)\n",
                 fin.out[0], fin.out[1], fin.out[2], fin.out[3], (long long)fin.iters);

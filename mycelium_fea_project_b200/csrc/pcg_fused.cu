@@ -1,22 +1,34 @@
-// K5, single-kernel form: the whole Jacobi-PCG solve is ONE persistent cooperative launch
-// (one 1024-thread block per SM).  Motivation (profiles/r1_pcg512_launches.md): on the
-// 512^2 benchmark operator (L2-resident) an iteration of the three-kernel PCG costs ~47 us of
-// which the SpMV body is only about half; the rest is launch gaps, per-kernel prologues and
-// last-block reductions.  Here an iteration is
+// K5, single-kernel form: the whole Jacobi-PCG solve is ONE persistent cooperative launch per GPU
+// (one 1024-thread block per SM), on one GPU or on several GPUs that talk through NVLink peer
+// memory -- no NCCL call, no host round trip and no kernel boundary inside the iteration loop.
 //
+// Per iteration (single-reduction recurrence of Chronopoulos & Gear):
 //   A. w = K u + reg u   (TMA-pipelined sweep, spmv_tma.cuh) with gamma = r.u, delta = w.u and
-//      r.r folded into the epilogue                                   -> grid barrier + reduce
+//      r.r folded into the epilogue                                  -> barrier #1 (+ reduction)
 //   B. beta = gamma/gamma_old, alpha = gamma/(delta - beta gamma/alpha_old)
-//      p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;  u = M^-1 r   -> grid barrier
+//      p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;  u = M^-1 r
+//      -- rows that a neighbouring GPU gathers are ALSO stored straight into that GPU's u buffer
+//      (same global offset, P2P store over NVLink)                   -> barrier #2 (halo ready)
 //
-// i.e. the single-reduction recurrence of Chronopoulos & Gear (one global reduction and two
-// grid barriers per iteration instead of two reductions and four launches).  The matrix stream
-// never stops: each warp requests the first tile of the next sweep before it enters phase B.
-// Scalars are reduced from per-block partials in a fixed order by every block, so all blocks
-// take identical decisions and the result is bit-reproducible for a given grid.
-// The gathered vector u is rewritten every iteration by other SMs: it is read with ordinary
-// (L1-coherent-after-fence) loads, never through ld.global.nc, and the acquiring
-// __threadfence() of the grid barrier invalidates the SM's L1.
+// Barriers are "arrive / leader / release": every block arrives on a local counter, the last
+// arriver's warp 0 does the cross-GPU part, then releases the local blocks.
+//   #1: the leader sums the per-block partials in a fixed order, stores the three local totals
+//       into every rank's PeerSync slot, raises its reduction flag there, waits for all ranks'
+//       flags and adds the slots in rank order -> every GPU obtains bit-identical global sums and
+//       therefore takes identical decisions (convergence, breakdown, maxit).
+//   #2: the leader raises its halo flag at the neighbours that read its rows and waits for the
+//       neighbours it reads from.
+// The all-rank barrier #1 sits between a sweep (which reads the halo) and the pushes of the next
+// values, so the halo needs no double buffering; the reduction slots are double-buffered by
+// parity because only neighbours are synchronised by #2.  Flags are monotone epochs that continue
+// across solves.  Every spin is bounded and traps instead of hanging the GPU.
+// The matrix stream never stops: each warp requests the first tile of the next sweep before it
+// enters phase B.  u is read with ordinary loads (never ld.global.nc); the acquiring
+// __threadfence() after each barrier invalidates the SM's L1.
+//
+// Measured motivation (profiles/r1_pcg_fused.md): on the L2-resident 512^2 benchmark operator the
+// three-kernel PCG costs ~47 us per iteration, about half of it launch gaps, per-kernel prologues
+// and last-block reductions; with NCCL (halo + 2 all-reduces) ~78 us at 2 GPUs.
 #include "common.cuh"
 #include "spmv.cuh"
 #include "spmv_tma.cuh"
@@ -27,42 +39,87 @@ constexpr int FU_WARPS = 32;
 constexpr int FU_THREADS = 32 * FU_WARPS;
 constexpr size_t FU_SMEM_BYTES = FU_WARPS * TM_SMEM_PER_WARP + FU_WARPS * TM_STAGES * sizeof(uint64_t) + 128;
 
+struct PeerSync {                       // lives behind the u vector in each rank's IPC-shared buffer
+  double sums[2][MYC_MAX_WORLD][4];     // [parity][writer rank][gamma, delta, r.r, -]
+  unsigned flag_red[MYC_MAX_WORLD];     // written by rank q: reductions q has published
+  unsigned flag_halo[MYC_MAX_WORLD];    // written by rank q: phase-B passes q has completed
+};
+
 struct FusedArgs {
-  int64_t n_rows;
+  int64_t n_rows, row_offset;
   const int32_t* rp;
   const int32_t* ci;
   const double* v;
   const double* dinv;
   double* x;
   double* r;
-  double* u;      // gathered vector (n_rows)
   double* w;
   double* p;
   double* s;
   double reg;
   long long maxit;
-  double* partials;     // [gridDim][3]
-  unsigned* bar_counter;
-  PcgScalars* sc;       // in: bb, tol2 ; out: iters, rr_final, done, breakdown
+  double* partials;        // [gridDim][3]
+  unsigned* bar;           // [0] arrive counter, [1] release epoch (both zeroed before the launch)
+  double* gsum;            // [2][4] global sums published by the leader
+  PcgScalars* sc;          // in: tol2 ; out: iters, rr_final, done, breakdown, final epochs
+  int world, rank;
+  unsigned epoch_red0, epoch_halo0;            // epochs reached by previous solves
+  double* peer_u[MYC_MAX_WORLD];               // u buffers (global length); [rank] is the local one
+  PeerSync* peer_sync[MYC_MAX_WORLD];
+  int64_t give_lo[MYC_MAX_WORLD], give_hi[MYC_MAX_WORLD];   // DOF ranges of MY rows that peer q gathers
+  unsigned char recv_any[MYC_MAX_WORLD];       // I gather rows of peer q
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+constexpr unsigned FU_SPIN_LIMIT = 1u << 28;
+
+// arrive / leader / release barrier.  `leader_work(lane)` runs on warp 0 of the last-arriving block.
+template <class F>
+__device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoch, int* s_leader, F&& leader_work) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
   if (threadIdx.x == 0) {
-    target += gridDim.x;
-    __threadfence();                        // release: this block's stores are visible gpu-wide
-    atomicAdd(counter, 1u);
+    ++epoch;
+    if (a.world > 1) __threadfence_system(); else __threadfence();      // release this block's stores
+    const unsigned old = atomicAdd(&a.bar[0], 1u);
+    *s_leader = (old == epoch * gridDim.x - 1u);
+  }
+  __syncthreads();
+  if (*s_leader && warp == 0) {
+    __threadfence();
+    leader_work(lane);
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      st_release_gpu(&a.bar[1], epoch);
+    }
+  }
+  if (threadIdx.x == 0) {
     unsigned spins = 0;
-    while (ld_acquire_u32(counter) < target) {
-      if (++spins > (1u << 27)) __trap();   // co-residency is guaranteed by the cooperative launch;
-    }                                       // a lost block must fail loudly, not hang the GPU
-    __threadfence();                        // acquire + L1 invalidate (CCTL.IVALL)
+    while (ld_acquire_gpu(&a.bar[1]) < epoch)
+      if (++spins > FU_SPIN_LIMIT) __trap();
+    __threadfence();                                                     // acquire + L1 invalidate
   }
   __syncthreads();
 }
@@ -70,11 +127,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
 struct EpiFused {   // w = K u + reg u ; acc = {r.u, w.u, r.r}
   static constexpr int NACC = 3;
   double* w;
-  const double* u;
+  const double* u_own;   // u + row_offset
   const double* r;
   double reg;
   struct Pre { double ui, ri; };
-  __device__ __forceinline__ Pre load(int64_t i) const { return Pre{u[i], r[i]}; }
+  __device__ __forceinline__ Pre load(int64_t i) const { return Pre{u_own[i], r[i]}; }
   __device__ __forceinline__ void row(int64_t i, double sum, const Pre& pre, double (&acc)[3]) const {
     const double ui = pre.ui, ri = pre.ri;
     const double wi = sum + reg * ui;
@@ -85,12 +142,12 @@ struct EpiFused {   // w = K u + reg u ; acc = {r.u, w.u, r.r}
   }
 };
 
+#ifdef MYC_FUSED_TIMING
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#ifdef MYC_FUSED_TIMING
 #define FT_MARK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long n_ = gtimer(); tacc[k] += n_ - tlast; tlast = n_; } } while (0)
 #else
 #define FT_MARK(k) do { } while (0)
@@ -100,12 +157,16 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   extern __shared__ __align__(128) unsigned char fu_smem[];
   __shared__ double s_red[FU_WARPS][3];
   __shared__ double s_tot[3];
+  __shared__ int s_leader;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n = a.n_rows;
   const int64_t gtid = (int64_t)blockIdx.x * FU_THREADS + threadIdx.x;
   const int64_t gstride = (int64_t)gridDim.x * FU_THREADS;
   const double tol2 = a.sc->tol2;
-  unsigned bar_target = 0;
+  unsigned epoch = 0;                                  // local barrier epoch
+  unsigned ep_red = a.epoch_red0, ep_halo = a.epoch_halo0;
+  double* const u = a.peer_u[a.rank];
+  PeerSync* const my_sync = a.peer_sync[a.rank];
 
   TmPipe pp;
   tm_pipe_init(pp, fu_smem, FU_WARPS, warp, lane);
@@ -113,13 +174,41 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   const int64_t gw = (int64_t)blockIdx.x * FU_WARPS + warp;
   const int64_t n_warps = (int64_t)gridDim.x * FU_WARPS;
 
+  // store one entry of u locally and into every GPU that gathers it
+  auto put_u = [&](int64_t i, double val) {
+    const int64_t g = a.row_offset + i;
+    u[g] = val;
+    if (a.world > 1) {
+#pragma unroll 1
+      for (int q = 0; q < a.world; ++q)
+        if (g >= a.give_lo[q] && g < a.give_hi[q]) a.peer_u[q][g] = val;
+    }
+  };
+  // barrier #2: phase-B results (and the pushed halo) are complete everywhere they are needed
+  auto halo_barrier = [&]() {
+    ++ep_halo;
+    const unsigned e = ep_halo;
+    fused_barrier(a, epoch, &s_leader, [&](int ln) {
+      if (a.world > 1 && ln == 0) {
+        for (int q = 0; q < a.world; ++q)
+          if (q != a.rank && a.give_hi[q] > a.give_lo[q]) st_release_sys(&a.peer_sync[q]->flag_halo[a.rank], e);
+        for (int q = 0; q < a.world; ++q)
+          if (q != a.rank && a.recv_any[q]) {
+            unsigned spins = 0;
+            while (ld_acquire_sys(&my_sync->flag_halo[q]) < e)
+              if (++spins > FU_SPIN_LIMIT) __trap();
+          }
+      }
+    });
+  };
+
   // init: u = M^-1 r, p = s = 0
   for (int64_t i = gtid; i < n; i += gstride) {
-    a.u[i] = a.dinv[i] * a.r[i];
+    put_u(i, a.dinv[i] * a.r[i]);
     a.p[i] = 0.0;
     a.s[i] = 0.0;
   }
-  grid_barrier(a.bar_counter, bar_target);
+  halo_barrier();
 
 #ifdef MYC_FUSED_TIMING
   unsigned long long tacc[4] = {0, 0, 0, 0}, tlast = gtimer();
@@ -127,11 +216,11 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   double gamma_old = 1.0, alpha_old = 1.0, rr = 0.0;
   long long it = 0;
   int status = 0;   // 1 converged, 2 breakdown, 0 maxit
-  EpiFused epi{a.w, a.u, a.r, a.reg};
+  EpiFused epi{a.w, u + a.row_offset, a.r, a.reg};
   for (;;) {
     // ---- phase A: w = A u, partial dots
     double acc[3] = {0.0, 0.0, 0.0};
-    tm_warp_sweep<EpiFused, true, true>(pp, n, a.rp, a.ci, a.v, a.u, epi, acc, gw, n_warps, lane, nnz_total);
+    tm_warp_sweep<EpiFused, true, true>(pp, n, a.rp, a.ci, a.v, u, epi, acc, gw, n_warps, lane, nnz_total);
     FT_MARK(0);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -146,18 +235,44 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
       for (int wq = 0; wq < FU_WARPS; ++wq) t += s_red[wq][threadIdx.x];
       a.partials[(size_t)blockIdx.x * 3 + threadIdx.x] = t;
     }
-    grid_barrier(a.bar_counter, bar_target);
-    // every block sums the per-block partials in the same fixed order
-    if (warp == 0) {
+    // ---- barrier #1 with the (cross-GPU) reduction done by the leader
+    ++ep_red;
+    const unsigned er = ep_red;
+    const int par = (int)(er & 1u);
+    fused_barrier(a, epoch, &s_leader, [&](int ln) {
+      double tot[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         double t = 0.0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(&a.partials[(size_t)b * 3 + j]);
+        for (unsigned b = ln; b < gridDim.x; b += 32) t += __ldcg(&a.partials[(size_t)b * 3 + j]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) s_tot[j] = t;
+        tot[j] = t;
       }
-    }
+      if (a.world > 1) {
+        if (ln == 0) {
+          for (int q = 0; q < a.world; ++q) {
+            double* slot = a.peer_sync[q]->sums[par][a.rank];
+            slot[0] = tot[0]; slot[1] = tot[1]; slot[2] = tot[2];
+          }
+          __threadfence_system();
+          for (int q = 0; q < a.world; ++q) st_release_sys(&a.peer_sync[q]->flag_red[a.rank], er);
+          for (int q = 0; q < a.world; ++q) {
+            unsigned spins = 0;
+            while (ld_acquire_sys(&my_sync->flag_red[q]) < er)
+              if (++spins > FU_SPIN_LIMIT) __trap();
+          }
+          for (int j = 0; j < 3; ++j) {
+            double t = 0.0;
+            for (int q = 0; q < a.world; ++q) t += ld_volatile_f64(&my_sync->sums[par][q][j]);   // rank order
+            a.gsum[par * 4 + j] = t;
+          }
+        }
+      } else if (ln == 0) {
+        a.gsum[par * 4 + 0] = tot[0]; a.gsum[par * 4 + 1] = tot[1]; a.gsum[par * 4 + 2] = tot[2];
+      }
+    });
+    if (threadIdx.x < 3) s_tot[threadIdx.x] = __ldcg(&a.gsum[par * 4 + threadIdx.x]);
     __syncthreads();
     FT_MARK(1);
     const double gamma = s_tot[0], delta = s_tot[1];
@@ -171,20 +286,20 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     // ---- phase B: all vector recurrences in one pass
     for (int64_t i = gtid; i < n; i += gstride) {
       const double d = a.dinv[i];
-      const double pi = a.u[i] + beta * a.p[i];
+      const double pi = u[a.row_offset + i] + beta * a.p[i];
       const double si = a.w[i] + beta * a.s[i];
       a.p[i] = pi;
       a.s[i] = si;
       a.x[i] += alpha * pi;
       const double ri = d != 0.0 ? a.r[i] - alpha * si : 0.0;
       a.r[i] = ri;
-      a.u[i] = d * ri;
+      put_u(i, d * ri);
     }
     gamma_old = gamma;
     alpha_old = alpha;
     ++it;
     FT_MARK(2);
-    grid_barrier(a.bar_counter, bar_target);
+    halo_barrier();
     FT_MARK(3);
   }
   // drain the prefetched head tile so that no bulk copy is in flight when the block exits
@@ -207,23 +322,80 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     a.sc->red[1] = rr;
     a.sc->done = (status == 1);
     a.sc->breakdown = (status == 2);
+    a.sc->pAp = (double)ep_red;          // final epochs, carried into the next solve by the host
+    a.sc->rz_old = (double)ep_halo;
 #ifdef MYC_FUSED_TIMING
     for (int k = 0; k < 4; ++k) a.sc->out[k] = (double)tacc[k] / (double)(it > 0 ? it : 1);   // ns per iteration
 #endif
   }
 }
 
+size_t peer_buffer_bytes(int64_t cap) { return ((size_t)cap * sizeof(double) + 255) / 256 * 256 + sizeof(PeerSync); }
+PeerSync* peer_sync_of(void* base, int64_t cap) {
+  return (PeerSync*)((char*)base + ((size_t)cap * sizeof(double) + 255) / 256 * 256);
+}
+
 }  // namespace
+
+// ---- peer-memory setup (multi-GPU) -----------------------------------------------------------
+extern "C" int myc_dist_peer_alloc(myc_ctx* ctx, int64_t n_cols_capacity, uint8_t* h_out_handle64) {
+  if (!ctx || !h_out_handle64 || n_cols_capacity < 0) return MYC_ERR_BAD_ARG;
+  if (ctx->world > MYC_MAX_WORLD) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "peer path supports at most %d ranks", MYC_MAX_WORLD);
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  MYC_CUDA(ctx, cudaDeviceSynchronize());
+  for (int q = 0; q < MYC_MAX_WORLD; ++q) {
+    if (ctx->peer_base[q] && q != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_base[q]);
+    ctx->peer_base[q] = nullptr;
+  }
+  if (ctx->peer_own) MYC_CUDA(ctx, cudaFree(ctx->peer_own));
+  ctx->peer_own = nullptr;
+  ctx->peer_ok = false;
+  const size_t bytes = peer_buffer_bytes(n_cols_capacity);
+  MYC_CUDA(ctx, cudaMalloc(&ctx->peer_own, bytes));
+  MYC_CUDA(ctx, cudaMemset(ctx->peer_own, 0, bytes));
+  MYC_CUDA(ctx, cudaDeviceSynchronize());
+  ctx->peer_cap = n_cols_capacity;
+  cudaIpcMemHandle_t h;
+  MYC_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->peer_own));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(h_out_handle64, &h, 64);
+  return MYC_OK;
+}
+
+extern "C" int myc_dist_peer_open(myc_ctx* ctx, const uint8_t* h_handles) {
+  if (!ctx || !h_handles) return MYC_ERR_BAD_ARG;
+  if (!ctx->peer_own) MYC_FAIL(ctx, MYC_ERR_STATE, "peer_open: call myc_dist_peer_alloc first");
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int q = 0; q < ctx->world; ++q) {
+    if (q == ctx->rank) { ctx->peer_base[q] = ctx->peer_own; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handles + 64 * (size_t)q, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      MYC_FAIL(ctx, MYC_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) -> %s (no P2P path: the NCCL PCG is used instead)", q,
+               cudaGetErrorString(e));
+    }
+    ctx->peer_base[q] = p;
+  }
+  ctx->peer_epoch_red = ctx->peer_epoch_halo = 0;
+  ctx->peer_ok = true;
+  return MYC_OK;
+}
 
 // Returns MYC_OK and fills *handled = 1 if the fused path ran; *handled = 0 means "not applicable
 // here" (caller falls back to the multi-kernel PCG).  On entry r = b - A x0 is in ctx->vec[1] and
-// sc->bb / sc->tol2 / sc->done are set (pcg.cu does that for both paths).
-int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, const int32_t* d_row_ptr, const int32_t* d_col_idx,
-                      const double* d_val, const double* d_dinv, double reg, int64_t maxit, double* d_x,
-                      cudaStream_t st, int* handled) {
+// sc->tol2 is set (pcg.cu does that for both paths).
+int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
+                      const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
+                      const double* d_dinv, double reg, int64_t maxit, double* d_x, cudaStream_t st, int* handled) {
   *handled = 0;
-  if (ctx->world > 1 || ctx->no_fused_pcg || n_rows == 0) return MYC_OK;
-  if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;
+  if (ctx->no_fused_pcg) return MYC_OK;
+  const bool dist = ctx->world > 1;
+  if (dist && (!ctx->peer_ok || ctx->peer_cap < n_cols_global || ctx->world > MYC_MAX_WORLD)) return MYC_OK;
+  if (!dist && n_rows == 0) return MYC_OK;
+  if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;   // (same allocator on every rank)
   static int max_blocks_per_sm = -1;
   if (max_blocks_per_sm < 0) {
     MYC_CUDA(ctx, cudaFuncSetAttribute(pcg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
@@ -233,36 +405,55 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, const int32_t* d_row_ptr, co
   int coop = 0;
   MYC_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   if (max_blocks_per_sm < 1 || !coop) return MYC_OK;
-  // work vectors: u, w, p, s (r is vec[1])
-  MYC_TRY(myc_ensure(ctx, ctx->vec[0], (size_t)(n_rows + 1) * sizeof(double)));
+  // work vectors: w, p, s (r is vec[1]); u is vec[0] on one GPU, the IPC-shared buffer otherwise
+  if (!dist) MYC_TRY(myc_ensure(ctx, ctx->vec[0], (size_t)(n_cols_global + 1) * sizeof(double)));
   MYC_TRY(myc_ensure(ctx, ctx->vec[2], (size_t)(n_rows + 1) * sizeof(double)));
   MYC_TRY(myc_ensure(ctx, ctx->vec[3], (size_t)(n_rows + 1) * sizeof(double)));
   MYC_TRY(myc_ensure(ctx, ctx->vec[5], (size_t)(n_rows + 1) * sizeof(double)));
-  MYC_TRY(myc_ensure(ctx, ctx->misc, 256));
+  MYC_TRY(myc_ensure(ctx, ctx->misc, 512));
+  MYC_TRY(myc_ensure(ctx, ctx->partials, (size_t)ctx->sm_count * 16 * 4 * sizeof(double)));
   const int64_t n_tiles = ceil_div64(n_rows, TM_ROWS);
   int grid = ctx->sm_count;
   if (ceil_div64(n_tiles, FU_WARPS) < grid) grid = (int)ceil_div64(n_tiles, FU_WARPS);
   if (grid < 1) grid = 1;
-  MYC_TRY(myc_ensure(ctx, ctx->partials, (size_t)ctx->sm_count * 16 * 4 * sizeof(double)));
-  unsigned* bar = (unsigned*)((char*)ctx->misc.p + 224);
-  MYC_CUDA(ctx, cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+  unsigned* bar = (unsigned*)((char*)ctx->misc.p + 224);          // [0] counter [1] release
+  double* gsum = (double*)((char*)ctx->misc.p + 256);             // [2][4]
+  MYC_CUDA(ctx, cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
   FusedArgs a;
+  memset(&a, 0, sizeof(a));
   a.n_rows = n_rows;
+  a.row_offset = row_offset;
   a.rp = d_row_ptr;
   a.ci = d_col_idx;
   a.v = d_val;
   a.dinv = d_dinv;
   a.x = d_x;
   a.r = (double*)ctx->vec[1].p;
-  a.u = (double*)ctx->vec[0].p;
   a.w = (double*)ctx->vec[2].p;
   a.p = (double*)ctx->vec[3].p;
   a.s = (double*)ctx->vec[5].p;
   a.reg = reg;
   a.maxit = (long long)maxit;
   a.partials = (double*)ctx->partials.p;
-  a.bar_counter = bar;
+  a.bar = bar;
+  a.gsum = gsum;
   a.sc = (PcgScalars*)ctx->scalars.p;
+  a.world = ctx->world;
+  a.rank = ctx->rank;
+  if (dist) {
+    a.epoch_red0 = ctx->peer_epoch_red;
+    a.epoch_halo0 = ctx->peer_epoch_halo;
+    for (int q = 0; q < ctx->world; ++q) {
+      a.peer_u[q] = (double*)ctx->peer_base[q];
+      a.peer_sync[q] = peer_sync_of(ctx->peer_base[q], ctx->peer_cap);
+      a.give_lo[q] = q == ctx->rank ? 0 : ctx->send_to[q].lo;
+      a.give_hi[q] = q == ctx->rank ? 0 : ctx->send_to[q].hi;
+      a.recv_any[q] = (q != ctx->rank && ctx->recv_from[q].hi > ctx->recv_from[q].lo) ? 1 : 0;
+    }
+  } else {
+    a.peer_u[0] = (double*)ctx->vec[0].p;
+    a.peer_sync[0] = nullptr;
+  }
   void* params[] = {&a};
   MYC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel, dim3(grid), dim3(FU_THREADS), params,
                                             FU_SMEM_BYTES, st));

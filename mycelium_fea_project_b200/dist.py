@@ -171,6 +171,35 @@ class DistributedSolver:
         check(self.ctx.h, lib.myc_dist_set_plan(self.ctx.h, *[a.ctypes.data_as(C.c_void_p) for a in keep]))
         self.ctx.node_offsets = p.offsets
 
+    def _ensure_peer(self, n_cols):
+        """Set up (or grow) the NVLink peer-memory buffers of the fused multi-GPU PCG.  Collective.
+        If any rank cannot open a peer handle every rank falls back to the NCCL loop."""
+        import os
+        import torch
+        import torch.distributed as dist
+        from ._lib import lib, check
+        if self.world == 1 or os.environ.get("MYC_NO_PEER") == "1":
+            return
+        if getattr(self.ctx, "peer_cap", 0) >= n_cols:
+            return
+        cap = int(n_cols * 1.05) + 1024
+        handle = np.zeros(64, dtype=np.uint8)
+        check(self.ctx.h, lib.myc_dist_peer_alloc(self.ctx.h, cap, handle.ctypes.data_as(C.c_void_p)))
+        t = torch.from_numpy(handle).to(self.ctx.device)
+        gathered = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(gathered, t)
+        allh = np.ascontiguousarray(np.concatenate([g.cpu().numpy() for g in gathered]))
+        rc = lib.myc_dist_peer_open(self.ctx.h, allh.ctypes.data_as(C.c_void_p))
+        ok = torch.tensor([1 if rc == 0 else 0], device=self.ctx.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            lib.myc_dist_peer_disable(self.ctx.h)
+            self.ctx.peer_cap = 1 << 62          # do not retry
+            self.ctx.peer_enabled = False
+        else:
+            self.ctx.peer_cap = cap
+            self.ctx.peer_enabled = True
+
     def assemble(self, E, A, I):
         from . import device as dv
         self._install_plan()
@@ -188,6 +217,7 @@ class DistributedSolver:
         td = lambda a, dt: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
         kd, kv = td(known_dofs, np.int64), td(known_vals, np.float64)
         sysd = dv.apply_dirichlet(ctx, K, kd, kv, reg, block3=(precond == "block3"))
+        self._ensure_peer(K.n_cols)
         x, iters, relres = dv.pcg(ctx, K, sysd, precond=precond, rtol=rtol, maxit=maxit)
         U = dv.merge_solution(ctx, K, sysd, x)         # own rows of a zeroed global vector
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -21,8 +21,10 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, N, precond, ret):
+def _worker(rank, world, port, N, precond, ret, no_peer=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
+    if no_peer:
+        os.environ["MYC_NO_PEER"] = "1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -50,17 +52,26 @@ def _worker(rank, world, port, N, precond, ret):
         assert abs(out["total_force"] - tf) <= 1e-7 * abs(tf)
         tr = dv.true_residual(solver.ctx, K, out["system"], out["x"])
         assert tr <= 1e-11
-        ret[rank] = (out["iterations"], err, out["total_force"])
+        # a second load case on the same solver (epochs of the peer flags continue across solves)
+        kd2, kv2 = fs.build_bc(hi_n, lo_n, 0.01, -0.03)
+        out2 = solver.load_case(K, kd2, kv2, rtol=1e-12, precond=precond)
+        U2o = fo.solve_system(Ko, kd2, kv2)
+        err2 = np.linalg.norm(out2["U"].cpu().numpy() - U2o) / np.linalg.norm(U2o)
+        assert err2 <= 1e-8, err2
+        ret[rank] = (out["iterations"], err, out["total_force"], bool(getattr(solver.ctx, "peer_enabled", False)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precond", ["jacobi", "block3"])
-def test_two_gpu_solve_matches_oracle(precond):
+@pytest.mark.parametrize("precond,no_peer", [("jacobi", False), ("jacobi", True), ("block3", False)])
+def test_two_gpu_solve_matches_oracle(precond, no_peer):
+    """jacobi/False: fused persistent kernel over NVLink peer memory; jacobi/True and block3: NCCL loop."""
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), 96, precond, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 96, precond, ret, no_peer), nprocs=world, join=True)
     assert len(ret) == world
     assert ret[0][0] == ret[1][0]            # same iteration count on both ranks
     assert ret[0][2] == ret[1][2]            # identical all-reduced reaction
+    if precond == "jacobi" and not no_peer:
+        assert ret[0][3] and ret[1][3], "peer-memory path was not enabled on this box"
