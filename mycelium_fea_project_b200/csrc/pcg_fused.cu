@@ -95,13 +95,17 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
 constexpr unsigned FU_SPIN_LIMIT = 1u << 28;
 
 // arrive / leader / release barrier.  `leader_work(lane)` runs on warp 0 of the last-arriving block.
+// `sys_release`: this block stored into a peer GPU's memory since the last barrier, so its release
+// fence must have system scope (an NVLink round trip); blocks that only wrote local memory use the
+// cheaper gpu-scope fence.
 template <class F>
-__device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoch, int* s_leader, F&& leader_work) {
+__device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoch, int* s_leader, bool sys_release,
+                                              F&& leader_work) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
   if (threadIdx.x == 0) {
     ++epoch;
-    if (a.world > 1) __threadfence_system(); else __threadfence();      // release this block's stores
+    if (sys_release) __threadfence_system(); else __threadfence();      // release this block's stores
     const unsigned old = atomicAdd(&a.bar[0], 1u);
     *s_leader = (old == epoch * gridDim.x - 1u);
   }
@@ -175,20 +179,23 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   const int64_t n_warps = (int64_t)gridDim.x * FU_WARPS;
 
   // store one entry of u locally and into every GPU that gathers it
+  bool pushed = false;            // this thread stored into a peer since the last halo barrier
   auto put_u = [&](int64_t i, double val) {
     const int64_t g = a.row_offset + i;
     u[g] = val;
     if (a.world > 1) {
 #pragma unroll 1
       for (int q = 0; q < a.world; ++q)
-        if (g >= a.give_lo[q] && g < a.give_hi[q]) a.peer_u[q][g] = val;
+        if (g >= a.give_lo[q] && g < a.give_hi[q]) { a.peer_u[q][g] = val; pushed = true; }
     }
   };
   // barrier #2: phase-B results (and the pushed halo) are complete everywhere they are needed
   auto halo_barrier = [&]() {
     ++ep_halo;
     const unsigned e = ep_halo;
-    fused_barrier(a, epoch, &s_leader, [&](int ln) {
+    const bool block_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
+    pushed = false;
+    fused_barrier(a, epoch, &s_leader, block_pushed, [&](int ln) {
       if (a.world > 1 && ln == 0) {
         for (int q = 0; q < a.world; ++q)
           if (q != a.rank && a.give_hi[q] > a.give_lo[q]) st_release_sys(&a.peer_sync[q]->flag_halo[a.rank], e);
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     ++ep_red;
     const unsigned er = ep_red;
     const int par = (int)(er & 1u);
-    fused_barrier(a, epoch, &s_leader, [&](int ln) {
+    fused_barrier(a, epoch, &s_leader, false, [&](int ln) {
       double tot[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
