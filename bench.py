@@ -273,7 +273,7 @@ def run_ours(args):
         p = prob[c]
         if world > 1:
             K, r = p["last"]
-            info[c]["true_relres"] = dv.true_residual(ctx, K, r["system"], r["x"])
+            info[c]["true_relres"] = p["solver"].true_residual(K, r["system"], r["x"])   # installs this mesh's halo plan
         else:
             r = p["last"]
             info[c]["true_relres"] = dv.true_residual(ctx, r.K, r.system, r.x)

@@ -205,6 +205,12 @@ class DistributedSolver:
         self._install_plan()
         return dv.assemble(self.ctx, self.mesh, E, A, I, node_range=(self.plan.node_begin, self.plan.node_end))
 
+    def true_residual(self, K, system, x):
+        """||b - A x|| / ||b|| recomputed from scratch with THIS solver's halo plan (collective)."""
+        from . import device as dv
+        self._install_plan()
+        return dv.true_residual(self.ctx, K, system, x)
+
     def load_case(self, K, known_dofs, known_vals, react_dofs=None, rtol=1e-10, precond="jacobi",
                   maxit=500_000, reg=1e-12, gather_U=True):
         """Returns dict(U (global, on every rank if gather_U), iterations, relres, total_force)."""

@@ -21,7 +21,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, N, precond, ret, no_peer=False):
+def _worker(rank, world, port, N, precond, ret, no_peer=False, shape=None, case="Y"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     if no_peer:
         os.environ["MYC_NO_PEER"] = "1"
@@ -32,7 +32,8 @@ def _worker(rank, world, port, N, precond, ret, no_peer=False):
         from mycelium_fea_project_b200 import device as dv, dist as md, fea_solver as fs
         from mycelium_fea_project_b200.synth import synth_network
         from oracle import fea_oracle as fo
-        coords, n1, n2 = synth_network(N)
+        coords, n1, n2 = synth_network(N) if shape is None else synth_network(*shape)
+        axis, comp = fs.LOAD_CASES[case]
         solver = md.DistributedSolver((coords, n1, n2), device=torch.device("cuda", rank))
         K = solver.assemble(fs.E_mod, fs.A, fs.I)
         Ko = fo.assemble_global_stiffness(coords, n1, n2, np.ones(len(n1), bool))
@@ -41,19 +42,19 @@ def _worker(rank, world, port, N, precond, ret, no_peer=False):
         ref = Ko[lo:hi]
         assert np.array_equal(Ks.indptr, ref.indptr) and np.array_equal(Ks.indices, ref.indices)
         assert np.abs(Ks.data - ref.data).max() <= 1e-12 * np.abs(ref.data).max()
-        hi_n, lo_n = fs.grip_nodes(coords, 0.5)
-        kd, kv = fs.build_bc(hi_n, lo_n, 0.02, -0.02)
-        out = solver.load_case(K, kd, kv, react_dofs=3 * hi_n + 1, rtol=1e-12, precond=precond)
+        hi_n, lo_n = fs.grip_nodes(coords, 0.5, axis)
+        kd, kv = fs.build_bc(hi_n, lo_n, 0.02, -0.02, comp)
+        out = solver.load_case(K, kd, kv, react_dofs=3 * hi_n + comp, rtol=1e-12, precond=precond)
         U = out["U"].cpu().numpy()
         Uo = fo.solve_system(Ko, kd, kv)
         err = np.linalg.norm(U - Uo) / np.linalg.norm(Uo)
-        tf = fo.reactions(Ko, Uo, hi_n)
+        tf = (Ko @ Uo)[3 * hi_n + comp].sum()
         assert err <= 1e-8, err
         assert abs(out["total_force"] - tf) <= 1e-7 * abs(tf)
         tr = dv.true_residual(solver.ctx, K, out["system"], out["x"])
         assert tr <= 1e-11
         # a second load case on the same solver (epochs of the peer flags continue across solves)
-        kd2, kv2 = fs.build_bc(hi_n, lo_n, 0.01, -0.03)
+        kd2, kv2 = fs.build_bc(hi_n, lo_n, 0.01, -0.03, comp)
         out2 = solver.load_case(K, kd2, kv2, rtol=1e-12, precond=precond)
         U2o = fo.solve_system(Ko, kd2, kv2)
         err2 = np.linalg.norm(out2["U"].cpu().numpy() - U2o) / np.linalg.norm(U2o)
@@ -75,3 +76,17 @@ def test_two_gpu_solve_matches_oracle(precond, no_peer):
     assert ret[0][2] == ret[1][2]            # identical all-reduced reaction
     if precond == "jacobi" and not no_peer:
         assert ret[0][3] and ret[1][3], "peer-memory path was not enabled on this box"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs >= 4 CUDA devices")
+@pytest.mark.parametrize("case,no_peer", [("X", False), ("Y", False), ("X", True)])
+def test_four_gpu_strips(case, no_peer):
+    """Middle ranks have two neighbours; X: tall specimen with grips (known DOFs) on every rank,
+    Y: wide specimen with grips on the first and last rank only (the bench's weak-scaling shapes)."""
+    world = 4
+    shape = (4 * 40, 48) if case == "X" else (48, 4 * 40)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), 0, "jacobi", ret, no_peer, shape, case), nprocs=world, join=True)
+    assert len(ret) == world
+    assert len({v[0] for v in ret.values()}) == 1 and len({v[2] for v in ret.values()}) == 1
