@@ -86,6 +86,9 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ double ld_volatile_f64(const double* p) {
   double v;
   asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -112,6 +115,7 @@ __device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoc
   __syncthreads();
   if (*s_leader && warp == 0) {
     __threadfence();
+    __syncwarp();          // the other lanes' work is ordered after lane 0's observation of the arrivals
     leader_work(lane);
     __syncwarp();
     if (lane == 0) {
@@ -196,15 +200,15 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     const bool block_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
     pushed = false;
     fused_barrier(a, epoch, &s_leader, block_pushed, [&](int ln) {
-      if (a.world > 1 && ln == 0) {
-        for (int q = 0; q < a.world; ++q)
-          if (q != a.rank && a.give_hi[q] > a.give_lo[q]) st_release_sys(&a.peer_sync[q]->flag_halo[a.rank], e);
-        for (int q = 0; q < a.world; ++q)
-          if (q != a.rank && a.recv_any[q]) {
-            unsigned spins = 0;
-            while (ld_acquire_sys(&my_sync->flag_halo[q]) < e)
-              if (++spins > FU_SPIN_LIMIT) __trap();
-          }
+      // one lane per peer: all NVLink round trips overlap
+      if (a.world > 1 && ln < a.world && ln != a.rank) {
+        __threadfence_system();
+        if (a.give_hi[ln] > a.give_lo[ln]) st_relaxed_sys(&a.peer_sync[ln]->flag_halo[a.rank], e);
+        if (a.recv_any[ln]) {
+          unsigned spins = 0;
+          while (ld_acquire_sys(&my_sync->flag_halo[ln]) < e)
+            if (++spins > FU_SPIN_LIMIT) __trap();
+        }
       }
     });
   };
@@ -257,23 +261,21 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
         tot[j] = t;
       }
       if (a.world > 1) {
-        if (ln == 0) {
-          for (int q = 0; q < a.world; ++q) {
-            double* slot = a.peer_sync[q]->sums[par][a.rank];
-            slot[0] = tot[0]; slot[1] = tot[1]; slot[2] = tot[2];
-          }
+        // one lane per peer: publish the local totals everywhere, then collect everybody's
+        if (ln < a.world) {
+          double* slot = a.peer_sync[ln]->sums[par][a.rank];
+          slot[0] = tot[0]; slot[1] = tot[1]; slot[2] = tot[2];
           __threadfence_system();
-          for (int q = 0; q < a.world; ++q) st_release_sys(&a.peer_sync[q]->flag_red[a.rank], er);
-          for (int q = 0; q < a.world; ++q) {
-            unsigned spins = 0;
-            while (ld_acquire_sys(&my_sync->flag_red[q]) < er)
-              if (++spins > FU_SPIN_LIMIT) __trap();
-          }
-          for (int j = 0; j < 3; ++j) {
-            double t = 0.0;
-            for (int q = 0; q < a.world; ++q) t += ld_volatile_f64(&my_sync->sums[par][q][j]);   // rank order
-            a.gsum[par * 4 + j] = t;
-          }
+          st_relaxed_sys(&a.peer_sync[ln]->flag_red[a.rank], er);
+          unsigned spins = 0;
+          while (ld_acquire_sys(&my_sync->flag_red[ln]) < er)
+            if (++spins > FU_SPIN_LIMIT) __trap();
+        }
+        __syncwarp();
+        if (ln < 3) {
+          double t = 0.0;
+          for (int q = 0; q < a.world; ++q) t += ld_volatile_f64(&my_sync->sums[par][q][ln]);   // rank order
+          a.gsum[par * 4 + ln] = t;
         }
       } else if (ln == 0) {
         a.gsum[par * 4 + 0] = tot[0]; a.gsum[par * 4 + 1] = tot[1]; a.gsum[par * 4 + 2] = tot[2];
