@@ -23,8 +23,8 @@ int myc_dist_allreduce_dev(myc_ctx* ctx, double* d_buf, int n, cudaStream_t st);
 int myc_dist_halo(myc_ctx* ctx, double* d_x_global, cudaStream_t st);              // dist.cu
 int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
                       const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
-                      const double* d_dinv, double reg, int64_t maxit, double* d_x, cudaStream_t st,
-                      int* handled);                                                // pcg_fused.cu
+                      const double* d_dinv, const double* d_binv, double reg, int64_t maxit, double* d_x,
+                      cudaStream_t st, int* handled);                               // pcg_fused.cu
 
 namespace {
 
@@ -293,13 +293,13 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   MYC_CUDA(ctx, cudaMemcpyAsync(&sc->bb, &sc->out[1], sizeof(double), cudaMemcpyDeviceToDevice, st));
   pcg_set_tol_kernel<<<1, 1, 0, st>>>(sc, rtol, atol);
   MYC_LAUNCHED(ctx);
-  // ---- Jacobi: the whole iteration loop is one persistent cooperative kernel per GPU (NVLink peer
+  // ---- the whole iteration loop is one persistent cooperative kernel per GPU (NVLink peer
   // memory between GPUs); falls through to the multi-kernel / NCCL loop when not applicable
-  if (!block3) {
+  {
     int handled = 0;
     if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
-    MYC_TRY(myc_pcg_fused_try(ctx, n_rows, n_cols_global, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv, reg, maxit,
-                              d_x, st, &handled));
+    MYC_TRY(myc_pcg_fused_try(ctx, n_rows, n_cols_global, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv,
+                              block3 ? d_binv : nullptr, reg, maxit, d_x, st, &handled));
     if (handled) {
       if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
       MYC_CUDA(ctx, cudaMemcpyAsync(h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));

@@ -1,4 +1,4 @@
-// K5, single-kernel form: the whole Jacobi-PCG solve is ONE persistent cooperative launch per GPU
+// K5, single-kernel form: the whole (block-)Jacobi-PCG solve is ONE persistent cooperative launch per GPU
 // (one 1024-thread block per SM), on one GPU or on several GPUs that talk through NVLink peer
 // memory -- no NCCL call, no host round trip and no kernel boundary inside the iteration loop.
 //
@@ -51,6 +51,7 @@ struct FusedArgs {
   const int32_t* ci;
   const double* v;
   const double* dinv;
+  const double* binv;      // (n_rows/3, 9) block-Jacobi inverse, or null for point Jacobi
   double* x;
   double* r;
   double* w;
@@ -161,6 +162,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define FT_MARK(k) do { } while (0)
 #endif
 
+template <bool BLOCK3>
 __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   extern __shared__ __align__(128) unsigned char fu_smem[];
   __shared__ double s_red[FU_WARPS][3];
@@ -213,11 +215,32 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     });
   };
 
+  // z = M^-1 r for one node (block-Jacobi): 3x3 inverse block times the node's residual
+  auto block3_apply = [&](int64_t nd, const double (&rr)[3], double (&z)[3]) {
+    const double* m = a.binv + 9 * nd;
+    z[0] = m[0] * rr[0] + m[1] * rr[1] + m[2] * rr[2];
+    z[1] = m[3] * rr[0] + m[4] * rr[1] + m[5] * rr[2];
+    z[2] = m[6] * rr[0] + m[7] * rr[1] + m[8] * rr[2];
+  };
   // init: u = M^-1 r, p = s = 0
-  for (int64_t i = gtid; i < n; i += gstride) {
-    put_u(i, a.dinv[i] * a.r[i]);
-    a.p[i] = 0.0;
-    a.s[i] = 0.0;
+  if constexpr (BLOCK3) {
+    for (int64_t nd = gtid; nd < n / 3; nd += gstride) {
+      const double rr[3] = {a.r[3 * nd], a.r[3 * nd + 1], a.r[3 * nd + 2]};
+      double z[3];
+      block3_apply(nd, rr, z);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        put_u(3 * nd + c, z[c]);
+        a.p[3 * nd + c] = 0.0;
+        a.s[3 * nd + c] = 0.0;
+      }
+    }
+  } else {
+    for (int64_t i = gtid; i < n; i += gstride) {
+      put_u(i, a.dinv[i] * a.r[i]);
+      a.p[i] = 0.0;
+      a.s[i] = 0.0;
+    }
   }
   halo_barrier();
 
@@ -293,16 +316,36 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     if (!(denom > 0.0) || !isfinite(gamma)) { status = 2; break; }
     const double alpha = gamma / denom;
     // ---- phase B: all vector recurrences in one pass
-    for (int64_t i = gtid; i < n; i += gstride) {
-      const double d = a.dinv[i];
-      const double pi = u[a.row_offset + i] + beta * a.p[i];
-      const double si = a.w[i] + beta * a.s[i];
-      a.p[i] = pi;
-      a.s[i] = si;
-      a.x[i] += alpha * pi;
-      const double ri = d != 0.0 ? a.r[i] - alpha * si : 0.0;
-      a.r[i] = ri;
-      put_u(i, d * ri);
+    if constexpr (BLOCK3) {
+      for (int64_t nd = gtid; nd < n / 3; nd += gstride) {
+        double rr[3], z[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int64_t i = 3 * nd + c;
+          const double pi = u[a.row_offset + i] + beta * a.p[i];
+          const double si = a.w[i] + beta * a.s[i];
+          a.p[i] = pi;
+          a.s[i] = si;
+          a.x[i] += alpha * pi;
+          rr[c] = a.dinv[i] != 0.0 ? a.r[i] - alpha * si : 0.0;
+          a.r[i] = rr[c];
+        }
+        block3_apply(nd, rr, z);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) put_u(3 * nd + c, z[c]);
+      }
+    } else {
+      for (int64_t i = gtid; i < n; i += gstride) {
+        const double d = a.dinv[i];
+        const double pi = u[a.row_offset + i] + beta * a.p[i];
+        const double si = a.w[i] + beta * a.s[i];
+        a.p[i] = pi;
+        a.s[i] = si;
+        a.x[i] += alpha * pi;
+        const double ri = d != 0.0 ? a.r[i] - alpha * si : 0.0;
+        a.r[i] = ri;
+        put_u(i, d * ri);
+      }
     }
     gamma_old = gamma;
     alpha_old = alpha;
@@ -398,7 +441,8 @@ extern "C" int myc_dist_peer_open(myc_ctx* ctx, const uint8_t* h_handles) {
 // sc->tol2 is set (pcg.cu does that for both paths).
 int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
                       const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
-                      const double* d_dinv, double reg, int64_t maxit, double* d_x, cudaStream_t st, int* handled) {
+                      const double* d_dinv, const double* d_binv, double reg, int64_t maxit, double* d_x,
+                      cudaStream_t st, int* handled) {
   *handled = 0;
   if (ctx->no_fused_pcg) return MYC_OK;
   const bool dist = ctx->world > 1;
@@ -407,9 +451,12 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;   // (same allocator on every rank)
   static int max_blocks_per_sm = -1;
   if (max_blocks_per_sm < 0) {
-    MYC_CUDA(ctx, cudaFuncSetAttribute(pcg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
-    MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, pcg_fused_kernel, FU_THREADS,
-                                                                FU_SMEM_BYTES));
+    MYC_CUDA(ctx, cudaFuncSetAttribute(pcg_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
+    MYC_CUDA(ctx, cudaFuncSetAttribute(pcg_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
+    int b0 = 0, b1 = 0;
+    MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, pcg_fused_kernel<false>, FU_THREADS, FU_SMEM_BYTES));
+    MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, pcg_fused_kernel<true>, FU_THREADS, FU_SMEM_BYTES));
+    max_blocks_per_sm = b0 < b1 ? b0 : b1;
   }
   int coop = 0;
   MYC_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
@@ -436,6 +483,7 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   a.ci = d_col_idx;
   a.v = d_val;
   a.dinv = d_dinv;
+  a.binv = d_binv;
   a.x = d_x;
   a.r = (double*)ctx->vec[1].p;
   a.w = (double*)ctx->vec[2].p;
@@ -464,8 +512,8 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
     a.peer_sync[0] = nullptr;
   }
   void* params[] = {&a};
-  MYC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel, dim3(grid), dim3(FU_THREADS), params,
-                                            FU_SMEM_BYTES, st));
+  const void* fn = d_binv ? (const void*)pcg_fused_kernel<true> : (const void*)pcg_fused_kernel<false>;
+  MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FU_THREADS), params, FU_SMEM_BYTES, st));
   ctx->launches++;
   *handled = 1;
   return MYC_OK;

@@ -416,3 +416,24 @@ def test_ramp_letter_fixtures(name, golden_dir, tmp_path, monkeypatch):
         scale = np.abs(b.values).max()
         assert np.abs(a.values - b.values).max() <= 1e-8 * scale, f"{name}/{f}"
     assert os.path.isfile(tmp_path / "fea_results" / "runtime.txt")
+
+
+def test_ramp_real_snapshot_cascade(golden_dir, monkeypatch):
+    """results/sim_20251117_181147 (7,375 nodes, 25 disconnected components, duplicate elements) with
+    the COMMITTED constants through the GPU ramp: the 40-step failure cascade must equal the
+    reference's committed active_elements.csv, the force-displacement curve must agree to 1e-7."""
+    d = os.path.join(golden_dir, "ref_results", "sim_20251117_181147")
+    nodes = pd.read_csv(io.BytesIO(gzip.open(os.path.join(d, "nodes.csv.gz")).read()))
+    elems = pd.read_csv(io.BytesIO(gzip.open(os.path.join(d, "elements.csv.gz")).read()))
+    monkeypatch.setattr(fs, "PCG_RTOL", 1e-12)
+    rec = fs.fea_ramp(nodes[["x", "y", "z"]].values, elems["n1"].values, elems["n2"].values)
+    g = np.load(os.path.join(d, "fea_results", "active_elements.npz"))
+    gold = np.unpackbits(g["packed"], axis=1)[:, :int(g["n_elems"])].astype(bool)
+    mine = np.array(rec["active"])
+    assert mine.shape == gold.shape
+    assert np.array_equal(mine, gold), f"cascade differs at steps {np.nonzero((mine != gold).any(1))[0][:5]}"
+    fd = pd.read_csv(os.path.join(d, "fea_results", "force_displacement.csv"), float_precision="round_trip").values
+    got = np.array(rec["force_disp"])
+    assert np.array_equal(got[:, 0], fd[:, 0])
+    assert np.abs(got[:, 1] - fd[:, 1]).max() <= 1e-7 * np.abs(fd[:, 1]).max()
+    print("real snapshot ramp: iterations per step", rec["iterations"][:6], "...")
