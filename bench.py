@@ -399,7 +399,10 @@ def hbm_roofline(ctx, dv, fs, peak, peak_src, N=2048):
     ach = nbytes / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "myc_spmv_kernel<EpiPlain> (y = K x)", "workload": f"synthetic {N}x{N} grid",
             "n_rows": K.n_rows, "nnz": K.nnz, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src, "avg_launch_us": ms * 1e3,
+            "traffic": 1.251e9 if N == 2048 else None,
+            "traffic_source": "ncu --set full capture of this kernel on this operator: dram read 1.207 GB + write "
+                              "0.044 GB per launch (profiles/r1_spmv2048_ncu.md); static, not re-measured here",
+            "peak_source": peak_src, "avg_launch_us": ms * 1e3,
             "algorithmic_bytes_per_launch": nbytes, "l2": "256 MiB flush write between launches"}
 
 
