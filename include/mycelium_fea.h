@@ -68,6 +68,16 @@ int64_t myc_launch_count(const myc_ctx* ctx);
 int myc_profile_reset(myc_ctx* ctx, int enable);
 int myc_profile_get(myc_ctx* ctx, double* h_out4);
 
+/* Structure hint for every CSR the caller passes from now on (sticky): non-zero = the matrix has
+ * the 3x3 node-block structure of this problem (3 DOF per node: the three rows of a node have equal
+ * length and their columns come in triples 3c,3c+1,3c+2 -- what myc_assemble_* emits), which lets
+ * the SpMV inside myc_spmv / myc_apply_dirichlet / myc_pcg_solve / myc_true_residual use one column
+ * index and one x gather per block.  A wrong hint gives wrong results; myc_csr_is_block3 verifies
+ * an arbitrary CSR on the device (one pass over col_idx). */
+int myc_set_csr_hint(myc_ctx* ctx, int node_block3);
+int myc_csr_is_block3(myc_ctx* ctx, int64_t n_rows, const int32_t* d_row_ptr, const int32_t* d_col_idx,
+                      int* h_out_is_block3, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1  element stiffness.  Replaces bar_stiffness_bulk(p1s,p2s,E,A,I) -> (K(N,6,6), L(N,))
  *     src/fea_solver.py:30-68   (C++ twin: element_stiffness_6x6, src/fea_petsc.cpp:88-140)

@@ -58,6 +58,8 @@ SIGNATURES = {
     "myc_destroy": [_p],
     "myc_last_error": [_p],
     "myc_launch_count": [_p],
+    "myc_set_csr_hint": [_p, _int],
+    "myc_csr_is_block3": [_p, _i64, _p, _p, C.POINTER(C.c_int), _p],
     "myc_profile_reset": [_p, _int],
     "myc_profile_get": [_p, _pf64],
     "myc_bar_stiffness_bulk": [_p, _p, _p, _i64, _f64, _f64, _f64, _p, _p, _p],

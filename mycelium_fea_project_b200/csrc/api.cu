@@ -30,6 +30,8 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
     ctx->force_plain_spmv = e && e[0] == '1';
     const char* f = getenv("MYC_NO_FUSED_PCG");
     ctx->no_fused_pcg = f && f[0] == '1';
+    const char* g = getenv("MYC_NO_BLOCK3_SPMV");
+    ctx->no_block3_spmv = g && g[0] == '1';
   }
   e = cudaSetDevice(device_ordinal);
   cudaDeviceProp prop;
@@ -66,6 +68,12 @@ extern "C" int myc_destroy(myc_ctx* ctx) {
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (cudaEvent_t e : ctx->prof_ev) if (e) cudaEventDestroy(e);
   delete ctx;
+  return MYC_OK;
+}
+
+extern "C" int myc_set_csr_hint(myc_ctx* ctx, int node_block3) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  ctx->csr_block3 = node_block3 != 0;
   return MYC_OK;
 }
 
@@ -148,6 +156,7 @@ extern "C" int myc_load_case_host(myc_ctx* ctx, const double* h_coords, const in
   int32_t* d_ci = (int32_t*)b[B_CI].p;
   double* d_val = (double*)b[B_VAL].p;
   MYC_TRY(myc_assemble_numeric(ctx, d_coords, d_n1, d_n2, E, A, I, nnz, d_rp, d_ci, d_val, st));
+  ctx->csr_block3 = true;     // what the assembler emits always has the node-block structure
   MYC_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
   MYC_TRY(myc_apply_dirichlet(ctx, n_dof, n_dof, 0, d_rp, d_ci, d_val, d_kd, d_kv, n_known, reg, d_ubc, d_rhs,
                               d_dinv, st));

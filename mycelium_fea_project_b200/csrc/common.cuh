@@ -29,6 +29,8 @@ struct myc_ctx {
   int64_t launches = 0;
   bool force_plain_spmv = false;   // MYC_FORCE_PLAIN_SPMV=1: use the non-TMA CSR-stream kernel
   bool no_fused_pcg = false;       // MYC_NO_FUSED_PCG=1: always use the multi-kernel PCG
+  bool no_block3_spmv = false;     // MYC_NO_BLOCK3_SPMV=1: ignore the node-block hint
+  bool csr_block3 = false;         // caller's hint: the CSR it passes has the 3x3 node-block structure
 
   // ---- scratch arenas (grown on demand, never shrunk)
   DevBuf scan_tmp;              // block sums of the exclusive scan (all levels)

@@ -110,6 +110,25 @@ reduced_fill_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
   }
 }
 
+// ---- structure check: does this CSR have the 3x3 node-block structure? ------------------------
+__global__ void __launch_bounds__(DI_THREADS)
+block3_check_kernel(int64_t n_nodes, const int32_t* __restrict__ rp, const int32_t* __restrict__ ci, int* __restrict__ bad) {
+  for (int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; nd < n_nodes; nd += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t s0 = rp[3 * nd], s1 = rp[3 * nd + 1], s2 = rp[3 * nd + 2], s3 = rp[3 * nd + 3];
+    const int32_t w = s1 - s0;
+    bool ok = (s2 - s1 == w) && (s3 - s2 == w) && (w % 3 == 0);
+    for (int32_t k = 0; ok && k < w; k += 3) {
+      const int32_t c = ci[s0 + k];
+      ok = (c % 3 == 0) && ci[s0 + k + 1] == c + 1 && ci[s0 + k + 2] == c + 2;
+      for (int a = 1; ok && a < 3; ++a) {
+        const int32_t o = s0 + a * w + k;
+        ok = ci[o] == c && ci[o + 1] == c + 1 && ci[o + 2] == c + 2;
+      }
+    }
+    if (!ok) *bad = 1;
+  }
+}
+
 // ---- 3x3 node-block inverse --------------------------------------------------------------
 __global__ void __launch_bounds__(DI_THREADS)
 block3_kernel(int64_t n_nodes_local, int64_t row_offset, const int32_t* __restrict__ rp,
@@ -189,6 +208,28 @@ extern "C" int myc_apply_dirichlet(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_
   MYC_CUDA(ctx, cudaMemcpyAsync(h, bad_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   MYC_CUDA(ctx, cudaStreamSynchronize(st));
   if (*h) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "apply_dirichlet: known DOF outside [0, n_dof)");
+  return MYC_OK;
+}
+
+extern "C" int myc_csr_is_block3(myc_ctx* ctx, int64_t n_rows, const int32_t* d_row_ptr, const int32_t* d_col_idx,
+                                 int* h_out_is_block3, void* stream) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  if (n_rows < 0 || !d_row_ptr || !h_out_is_block3) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "csr_is_block3: bad argument");
+  *h_out_is_block3 = 0;
+  if (n_rows % 3 != 0) return MYC_OK;
+  if (n_rows == 0) { *h_out_is_block3 = 1; return MYC_OK; }
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  MYC_TRY(myc_ensure(ctx, ctx->misc, 512));
+  int* bad = (int*)ctx->misc.p;
+  MYC_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(int), st));
+  block3_check_kernel<<<grid_for(ctx, ceil_div64(n_rows / 3, DI_THREADS), 8), DI_THREADS, 0, st>>>(n_rows / 3, d_row_ptr,
+                                                                                                  d_col_idx, bad);
+  MYC_LAUNCHED(ctx);
+  int* h = (int*)ctx->h_pinned;
+  MYC_CUDA(ctx, cudaMemcpyAsync(h, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MYC_CUDA(ctx, cudaStreamSynchronize(st));
+  *h_out_is_block3 = *h ? 0 : 1;
   return MYC_OK;
 }
 

@@ -162,7 +162,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define FT_MARK(k) do { } while (0)
 #endif
 
-template <bool BLOCK3>
+template <bool BLOCK3, class Cfg>
 __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   extern __shared__ __align__(128) unsigned char fu_smem[];
   __shared__ double s_red[FU_WARPS][3];
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   for (;;) {
     // ---- phase A: w = A u, partial dots
     double acc[3] = {0.0, 0.0, 0.0};
-    tm_warp_sweep<EpiFused, true, true>(pp, n, a.rp, a.ci, a.v, u, epi, acc, gw, n_warps, lane, nnz_total);
+    tm_warp_sweep<Cfg, EpiFused, true, true>(pp, n, a.rp, a.ci, a.v, u, epi, acc, gw, n_warps, lane, nnz_total);
     FT_MARK(0);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -354,20 +354,8 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     halo_barrier();
     FT_MARK(3);
   }
-  // drain the prefetched head tile so that no bulk copy is in flight when the block exits
-  if (pp.head_in_flight) {
-    const int64_t n_tiles = (n + TM_ROWS - 1) / TM_ROWS;
-    if (gw < n_tiles) {
-      const int64_t r0 = gw * TM_ROWS;
-      const int32_t lo = a.rp[r0];
-      const int64_t re = r0 + TM_ROWS < n ? r0 + TM_ROWS : n;
-      const int32_t hi = a.rp[re];
-      const int32_t a0 = lo & ~3;
-      int32_t a1 = (hi + 3) & ~3;
-      if (a1 > (nnz_total & ~3)) a1 = nnz_total & ~3;
-      if (hi > lo && hi - a0 <= TM_CAP && a1 > a0) tm_mbar_wait(&pp.bars[0], pp.phase_bits & 1u);
-    }
-  }
+  // no bulk copy may be in flight when the block exits
+  tm_pipe_drain<Cfg>(pp, n, a.rp, gw, nnz_total);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.sc->iters = it;
     a.sc->rr_final = rr;
@@ -451,12 +439,16 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;   // (same allocator on every rank)
   static int max_blocks_per_sm = -1;
   if (max_blocks_per_sm < 0) {
-    MYC_CUDA(ctx, cudaFuncSetAttribute(pcg_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
-    MYC_CUDA(ctx, cudaFuncSetAttribute(pcg_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
-    int b0 = 0, b1 = 0;
-    MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, pcg_fused_kernel<false>, FU_THREADS, FU_SMEM_BYTES));
-    MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, pcg_fused_kernel<true>, FU_THREADS, FU_SMEM_BYTES));
-    max_blocks_per_sm = b0 < b1 ? b0 : b1;
+    const void* fns[4] = {(const void*)pcg_fused_kernel<false, TmCfgGeneric>, (const void*)pcg_fused_kernel<true, TmCfgGeneric>,
+                          (const void*)pcg_fused_kernel<false, TmCfgBlock3>, (const void*)pcg_fused_kernel<true, TmCfgBlock3>};
+    int mn = 1 << 30;
+    for (const void* f : fns) {
+      int b = 0;
+      MYC_CUDA(ctx, cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
+      MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, f, FU_THREADS, FU_SMEM_BYTES));
+      mn = b < mn ? b : mn;
+    }
+    max_blocks_per_sm = mn;
   }
   int coop = 0;
   MYC_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
@@ -468,7 +460,8 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   MYC_TRY(myc_ensure(ctx, ctx->vec[5], (size_t)(n_rows + 1) * sizeof(double)));
   MYC_TRY(myc_ensure(ctx, ctx->misc, 512));
   MYC_TRY(myc_ensure(ctx, ctx->partials, (size_t)ctx->sm_count * 16 * 4 * sizeof(double)));
-  const int64_t n_tiles = ceil_div64(n_rows, TM_ROWS);
+  const bool b3 = ctx->csr_block3 && n_rows % 3 == 0 && !ctx->no_block3_spmv;
+  const int64_t n_tiles = ceil_div64(n_rows, b3 ? TmCfgBlock3::ROWS : TmCfgGeneric::ROWS);
   int grid = ctx->sm_count;
   if (ceil_div64(n_tiles, FU_WARPS) < grid) grid = (int)ceil_div64(n_tiles, FU_WARPS);
   if (grid < 1) grid = 1;
@@ -512,7 +505,8 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
     a.peer_sync[0] = nullptr;
   }
   void* params[] = {&a};
-  const void* fn = d_binv ? (const void*)pcg_fused_kernel<true> : (const void*)pcg_fused_kernel<false>;
+  const void* fn = b3 ? (d_binv ? (const void*)pcg_fused_kernel<true, TmCfgBlock3> : (const void*)pcg_fused_kernel<false, TmCfgBlock3>)
+                      : (d_binv ? (const void*)pcg_fused_kernel<true, TmCfgGeneric> : (const void*)pcg_fused_kernel<false, TmCfgGeneric>);
   MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FU_THREADS), params, FU_SMEM_BYTES, st));
   ctx->launches++;
   *handled = 1;

@@ -25,6 +25,11 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _hint(ctx, K):
+    """Tell the library whether the CSR about to be passed has the node-block structure."""
+    lib.myc_set_csr_hint(ctx.h, 1 if K.block3 else 0)
+
+
 class Context:
     """One myc_ctx per device (scratch arenas, NCCL communicator)."""
 
@@ -106,6 +111,7 @@ class DeviceCSR:
     row_ptr: torch.Tensor     # (n_rows+1,) i32
     col_idx: torch.Tensor     # (nnz,) i32
     val: torch.Tensor         # (nnz,) f64
+    block3: bool = False      # 3x3 node-block structure (always true for assembled K; verified otherwise)
 
     @property
     def nnz(self):
@@ -122,10 +128,16 @@ class DeviceCSR:
         K = K.tocsr()
         if not K.has_sorted_indices:
             K = K.sorted_indices()
-        return cls(K.shape[0], K.shape[1], 0,
-                   torch.from_numpy(K.indptr.astype(np.int32)).to(dev),
-                   torch.from_numpy(K.indices.astype(np.int32)).to(dev),
-                   torch.from_numpy(np.asarray(K.data, dtype=np.float64)).to(dev))
+        ctx = Context.get(device)
+        out = cls(K.shape[0], K.shape[1], 0,
+                  torch.from_numpy(K.indptr.astype(np.int32)).to(dev),
+                  torch.from_numpy(K.indices.astype(np.int32)).to(dev),
+                  torch.from_numpy(np.asarray(K.data, dtype=np.float64)).to(dev))
+        flag = C.c_int(0)
+        check(ctx.h, lib.myc_csr_is_block3(ctx.h, out.n_rows, _ptr(out.row_ptr), _ptr(out.col_idx), C.byref(flag),
+                                           _stream()))
+        out.block3 = bool(flag.value)
+        return out
 
 
 @dataclass
@@ -158,11 +170,12 @@ def assemble(ctx: Context, mesh: DeviceMesh, E, A, I, node_range=None) -> Device
     val = torch.empty((nnz.value,), dtype=torch.float64, device=ctx.device)
     check(ctx.h, lib.myc_assemble_numeric(ctx.h, _ptr(mesh.coords), _ptr(mesh.n1), _ptr(mesh.n2), float(E), float(A),
                                           float(I), nnz.value, _ptr(row_ptr), _ptr(col_idx), _ptr(val), _stream()))
-    return DeviceCSR(n_rows, 3 * mesh.n_nodes, 3 * nb, row_ptr, col_idx, val)
+    return DeviceCSR(n_rows, 3 * mesh.n_nodes, 3 * nb, row_ptr, col_idx, val, block3=True)
 
 
 def apply_dirichlet(ctx: Context, K: DeviceCSR, known_dofs: torch.Tensor, known_vals: torch.Tensor,
                     reg=REGULARISATION, block3=False) -> DirichletSystem:
+    _hint(ctx, K)
     ubc = torch.empty((K.n_cols,), dtype=torch.float64, device=ctx.device)
     rhs = torch.empty((K.n_rows,), dtype=torch.float64, device=ctx.device)
     dinv = torch.empty((K.n_rows,), dtype=torch.float64, device=ctx.device)
@@ -178,6 +191,7 @@ def apply_dirichlet(ctx: Context, K: DeviceCSR, known_dofs: torch.Tensor, known_
 
 
 def spmv(ctx: Context, K: DeviceCSR, x: torch.Tensor, out: torch.Tensor | None = None):
+    _hint(ctx, K)
     y = torch.empty((K.n_rows,), dtype=torch.float64, device=ctx.device) if out is None else out
     check(ctx.h, lib.myc_spmv(ctx.h, K.n_rows, _ptr(K.row_ptr), _ptr(K.col_idx), _ptr(K.val), _ptr(x), _ptr(y),
                               _stream()))
@@ -192,6 +206,7 @@ def pcg(ctx: Context, K: DeviceCSR, sys: DirichletSystem, x0: torch.Tensor | Non
     if pc == _lib.MYC_PC_BLOCK3 and sys.binv is None:
         raise ValueError("block3 preconditioner needs apply_dirichlet(..., block3=True)")
     iters, relres = C.c_int64(0), C.c_double(0.0)
+    _hint(ctx, K)
     rc = lib.myc_pcg_solve(ctx.h, K.n_rows, K.n_cols, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx), _ptr(K.val),
                            _ptr(sys.rhs), _ptr(sys.dinv), _ptr(sys.binv), pc, float(sys.reg), float(rtol),
                            float(atol), int(maxit), _ptr(x), C.byref(iters), C.byref(relres), _stream())
@@ -201,6 +216,7 @@ def pcg(ctx: Context, K: DeviceCSR, sys: DirichletSystem, x0: torch.Tensor | Non
 
 def true_residual(ctx: Context, K: DeviceCSR, sys: DirichletSystem, x: torch.Tensor) -> float:
     out = C.c_double(0.0)
+    _hint(ctx, K)
     check(ctx.h, lib.myc_true_residual(ctx.h, K.n_rows, K.n_cols, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx),
                                        _ptr(K.val), _ptr(sys.rhs), _ptr(sys.dinv), float(sys.reg), _ptr(x),
                                        C.byref(out), _stream()))
@@ -246,4 +262,4 @@ def reduce_csr(ctx: Context, K: DeviceCSR, sys: DirichletSystem):
                                     _ptr(free_index), _ptr(rrp), _ptr(rci), _ptr(rv), C.byref(n_free),
                                     C.byref(nnz2), _stream()))
     nf = int(n_free.value)
-    return DeviceCSR(nf, nf, 0, rrp[:nf + 1], rci, rv)
+    return DeviceCSR(nf, nf, 0, rrp[:nf + 1], rci, rv, block3=False)

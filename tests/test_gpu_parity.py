@@ -200,25 +200,51 @@ def test_spmv_matches_scipy(ctx):
     assert np.array_equal(y, y2)                                          # reproducible
 
 
-def test_spmv_tma_equals_plain_kernel(ctx, monkeypatch):
-    """The TMA-pipelined kernel and the plain CSR-stream kernel sum each row in the same order."""
+def test_spmv_kernel_variants_agree(ctx, monkeypatch):
+    """Three SpMV kernels on the same CSR: plain CSR-stream, TMA generic scheme (same per-row
+    summation order as the plain kernel -> identical bits) and TMA node-block scheme (one gather
+    per 3x3 block, partial sums per block -> same value to rounding, reproducible)."""
     coords, n1, n2 = synth_network(200, 173, seed=5)         # ragged sizes: partial tiles, nnz % 4 != 0
     Ko = fo.assemble_global_stiffness(coords, n1, n2, np.random.default_rng(2).random(len(n1)) > 0.1)
     Kd = dv.DeviceCSR.from_scipy(Ko)
+    assert Kd.block3                                          # verified on the device
     x = _dev(np.random.default_rng(3).standard_normal(Ko.shape[0]), np.float64)
-    y_tma = dv.spmv(ctx, Kd, x).cpu().numpy()
+    xh = x.cpu().numpy()
+    y_b3 = dv.spmv(ctx, Kd, x).cpu().numpy()
+    monkeypatch.setenv("MYC_NO_BLOCK3_SPMV", "1")
+    ctx_gen = dv.Context(0)
+    monkeypatch.delenv("MYC_NO_BLOCK3_SPMV")
     monkeypatch.setenv("MYC_FORCE_PLAIN_SPMV", "1")
-    ctx2 = dv.Context(0)
+    ctx_plain = dv.Context(0)
+    monkeypatch.delenv("MYC_FORCE_PLAIN_SPMV")
     try:
-        y_plain = dv.spmv(ctx2, Kd, x).cpu().numpy()
+        y_gen = dv.spmv(ctx_gen, Kd, x).cpu().numpy()
+        y_plain = dv.spmv(ctx_plain, Kd, x).cpu().numpy()
     finally:
-        ctx2.close()
-    assert np.array_equal(y_tma, y_plain)
-    assert np.abs(y_tma - Ko @ x.cpu().numpy()).max() <= 1e-14 * np.abs(Ko).dot(np.abs(x.cpu().numpy())).max()
-    for n in (1, 31, 32, 33, 95):                             # tiny matrices: fewer tiles than warps
+        ctx_gen.close(); ctx_plain.close()
+    assert np.array_equal(y_gen, y_plain)
+    scale = np.abs(Ko).dot(np.abs(xh)).max()
+    assert np.abs(y_b3 - y_plain).max() <= 1e-15 * scale
+    assert np.abs(y_plain - Ko @ xh).max() <= 1e-14 * scale
+    assert np.array_equal(y_b3, dv.spmv(ctx, Kd, x).cpu().numpy())       # reproducible
+    for n in (3, 30, 33, 54, 57, 96):                         # tiny matrices: fewer tiles than warps
         sub = Ko[:n, :].tocsr()
-        ys = dv.spmv(ctx, dv.DeviceCSR.from_scipy(sub), x).cpu().numpy()
-        assert np.allclose(ys, sub @ x.cpu().numpy(), rtol=1e-13, atol=1e-18)
+        Ks = dv.DeviceCSR.from_scipy(sub)
+        assert Ks.block3
+        ys = dv.spmv(ctx, Ks, x).cpu().numpy()
+        assert np.allclose(ys, sub @ xh, rtol=1e-13, atol=1e-18)
+    for n in (1, 31, 32):                                     # not a multiple of 3 -> generic scheme
+        sub = Ko[:n, :].tocsr()
+        Ks = dv.DeviceCSR.from_scipy(sub)
+        assert not Ks.block3
+        assert np.allclose(dv.spmv(ctx, Ks, x).cpu().numpy(), sub @ xh, rtol=1e-13, atol=1e-18)
+    # a matrix with 3k rows but without the node-block structure must be detected
+    from scipy.sparse import random as sprandom
+    M = sprandom(300, 300, density=0.03, format="csr", random_state=4); M.sort_indices()
+    Md = dv.DeviceCSR.from_scipy(M)
+    assert not Md.block3
+    xm = _dev(np.random.default_rng(9).standard_normal(300), np.float64)
+    assert np.allclose(dv.spmv(ctx, Md, xm).cpu().numpy(), M @ xm.cpu().numpy(), rtol=1e-12, atol=1e-14)
 
 
 def test_spmv_dense_rows_fallback(ctx):
