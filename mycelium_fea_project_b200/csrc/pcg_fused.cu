@@ -133,6 +133,22 @@ __device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoc
   __syncthreads();
 }
 
+// Single-GPU barrier: every block spins on the arrive counter itself (no leader hop).
+__device__ __forceinline__ void local_barrier(const FusedArgs& a, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++epoch;
+    __threadfence();
+    atomicAdd(&a.bar[0], 1u);
+    const unsigned target = epoch * gridDim.x;
+    unsigned spins = 0;
+    while (ld_acquire_gpu(&a.bar[0]) < target)
+      if (++spins > FU_SPIN_LIMIT) __trap();
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 struct EpiFused {   // w = K u + reg u ; acc = {r.u, w.u, r.r}
   static constexpr int NACC = 3;
   double* w;
@@ -162,7 +178,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define FT_MARK(k) do { } while (0)
 #endif
 
-template <bool BLOCK3, class Cfg>
+template <bool BLOCK3, class Cfg, bool DIST>
 __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   extern __shared__ __align__(128) unsigned char fu_smem[];
   __shared__ double s_red[FU_WARPS][3];
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   auto put_u = [&](int64_t i, double val) {
     const int64_t g = a.row_offset + i;
     u[g] = val;
-    if (a.world > 1) {
+    if constexpr (DIST) {
 #pragma unroll 1
       for (int q = 0; q < a.world; ++q)
         if (g >= a.give_lo[q] && g < a.give_hi[q]) { a.peer_u[q][g] = val; pushed = true; }
@@ -197,22 +213,26 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   };
   // barrier #2: phase-B results (and the pushed halo) are complete everywhere they are needed
   auto halo_barrier = [&]() {
-    ++ep_halo;
-    const unsigned e = ep_halo;
-    const bool block_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
-    pushed = false;
-    fused_barrier(a, epoch, &s_leader, block_pushed, [&](int ln) {
-      // one lane per peer: all NVLink round trips overlap
-      if (a.world > 1 && ln < a.world && ln != a.rank) {
-        __threadfence_system();
-        if (a.give_hi[ln] > a.give_lo[ln]) st_relaxed_sys(&a.peer_sync[ln]->flag_halo[a.rank], e);
-        if (a.recv_any[ln]) {
-          unsigned spins = 0;
-          while (ld_acquire_sys(&my_sync->flag_halo[ln]) < e)
-            if (++spins > FU_SPIN_LIMIT) __trap();
+    if constexpr (!DIST) {
+      local_barrier(a, epoch);
+    } else {
+      ++ep_halo;
+      const unsigned e = ep_halo;
+      const bool block_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
+      pushed = false;
+      fused_barrier(a, epoch, &s_leader, block_pushed, [&](int ln) {
+        // one lane per peer: all NVLink round trips overlap
+        if (ln < a.world && ln != a.rank) {
+          __threadfence_system();
+          if (a.give_hi[ln] > a.give_lo[ln]) st_relaxed_sys(&a.peer_sync[ln]->flag_halo[a.rank], e);
+          if (a.recv_any[ln]) {
+            unsigned spins = 0;
+            while (ld_acquire_sys(&my_sync->flag_halo[ln]) < e)
+              if (++spins > FU_SPIN_LIMIT) __trap();
+          }
         }
-      }
-    });
+      });
+    }
   };
 
   // z = M^-1 r for one node (block-Jacobi): 3x3 inverse block times the node's residual
@@ -269,21 +289,34 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
       for (int wq = 0; wq < FU_WARPS; ++wq) t += s_red[wq][threadIdx.x];
       a.partials[(size_t)blockIdx.x * 3 + threadIdx.x] = t;
     }
-    // ---- barrier #1 with the (cross-GPU) reduction done by the leader
-    ++ep_red;
-    const unsigned er = ep_red;
-    const int par = (int)(er & 1u);
-    fused_barrier(a, epoch, &s_leader, false, [&](int ln) {
-      double tot[3];
+    // ---- barrier #1 with the reduction
+    if constexpr (!DIST) {
+      local_barrier(a, epoch);
+      if (warp == 0) {              // every block sums the per-block partials in the same fixed order
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        double t = 0.0;
-        for (unsigned b = ln; b < gridDim.x; b += 32) t += __ldcg(&a.partials[(size_t)b * 3 + j]);
+        for (int j = 0; j < 3; ++j) {
+          double t = 0.0;
+          for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(&a.partials[(size_t)b * 3 + j]);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        tot[j] = t;
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) s_tot[j] = t;
+        }
       }
-      if (a.world > 1) {
+    } else {
+      // the leader (last-arriving block) reduces locally, exchanges with the peers, publishes
+      ++ep_red;
+      const unsigned er = ep_red;
+      const int par = (int)(er & 1u);
+      fused_barrier(a, epoch, &s_leader, false, [&](int ln) {
+        double tot[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          double t = 0.0;
+          for (unsigned b = ln; b < gridDim.x; b += 32) t += __ldcg(&a.partials[(size_t)b * 3 + j]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          tot[j] = t;
+        }
         // one lane per peer: publish the local totals everywhere, then collect everybody's
         if (ln < a.world) {
           double* slot = a.peer_sync[ln]->sums[par][a.rank];
@@ -300,11 +333,9 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
           for (int q = 0; q < a.world; ++q) t += ld_volatile_f64(&my_sync->sums[par][q][ln]);   // rank order
           a.gsum[par * 4 + ln] = t;
         }
-      } else if (ln == 0) {
-        a.gsum[par * 4 + 0] = tot[0]; a.gsum[par * 4 + 1] = tot[1]; a.gsum[par * 4 + 2] = tot[2];
-      }
-    });
-    if (threadIdx.x < 3) s_tot[threadIdx.x] = __ldcg(&a.gsum[par * 4 + threadIdx.x]);
+      });
+      if (threadIdx.x < 3) s_tot[threadIdx.x] = __ldcg(&a.gsum[par * 4 + threadIdx.x]);
+    }
     __syncthreads();
     FT_MARK(1);
     const double gamma = s_tot[0], delta = s_tot[1];
@@ -439,8 +470,10 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;   // (same allocator on every rank)
   static int max_blocks_per_sm = -1;
   if (max_blocks_per_sm < 0) {
-    const void* fns[4] = {(const void*)pcg_fused_kernel<false, TmCfgGeneric>, (const void*)pcg_fused_kernel<true, TmCfgGeneric>,
-                          (const void*)pcg_fused_kernel<false, TmCfgBlock3>, (const void*)pcg_fused_kernel<true, TmCfgBlock3>};
+    const void* fns[8] = {(const void*)pcg_fused_kernel<false, TmCfgGeneric, false>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, false>,
+                          (const void*)pcg_fused_kernel<false, TmCfgBlock3, false>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, false>,
+                          (const void*)pcg_fused_kernel<false, TmCfgGeneric, true>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, true>,
+                          (const void*)pcg_fused_kernel<false, TmCfgBlock3, true>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, true>};
     int mn = 1 << 30;
     for (const void* f : fns) {
       int b = 0;
@@ -505,8 +538,12 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
     a.peer_sync[0] = nullptr;
   }
   void* params[] = {&a};
-  const void* fn = b3 ? (d_binv ? (const void*)pcg_fused_kernel<true, TmCfgBlock3> : (const void*)pcg_fused_kernel<false, TmCfgBlock3>)
-                      : (d_binv ? (const void*)pcg_fused_kernel<true, TmCfgGeneric> : (const void*)pcg_fused_kernel<false, TmCfgGeneric>);
+  const int vi = (dist ? 4 : 0) + (b3 ? 2 : 0) + (d_binv ? 1 : 0);
+  const void* fns[8] = {(const void*)pcg_fused_kernel<false, TmCfgGeneric, false>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, false>,
+                        (const void*)pcg_fused_kernel<false, TmCfgBlock3, false>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, false>,
+                        (const void*)pcg_fused_kernel<false, TmCfgGeneric, true>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, true>,
+                        (const void*)pcg_fused_kernel<false, TmCfgBlock3, true>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, true>};
+  const void* fn = fns[vi];
   MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FU_THREADS), params, FU_SMEM_BYTES, st));
   ctx->launches++;
   *handled = 1;
