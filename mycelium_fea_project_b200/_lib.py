@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmycelium_fea_b200.so")
+LIB_PATH = os.environ.get("MYC_LIB_PATH") or os.path.join(_HERE, "libmycelium_fea_b200.so")   # override: A/B builds
 
 MYC_OK = 0
 MYC_ERR_BAD_ARG = -1

@@ -37,7 +37,6 @@ namespace {
 
 constexpr int FU_WARPS = 32;
 constexpr int FU_THREADS = 32 * FU_WARPS;
-constexpr size_t FU_SMEM_BYTES = FU_WARPS * TM_SMEM_PER_WARP + FU_WARPS * TM_STAGES * sizeof(uint64_t) + 128;
 
 struct PeerSync {                       // lives behind the u vector in each rank's IPC-shared buffer
   double sums[2][MYC_MAX_WORLD][4];     // [parity][writer rank][gamma, delta, r.r, -]
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   PeerSync* const my_sync = a.peer_sync[a.rank];
 
   TmPipe pp;
-  tm_pipe_init(pp, fu_smem, FU_WARPS, warp, lane);
+  tm_pipe_init(pp, fu_smem, FU_WARPS, warp, lane, Cfg::CAP);
   const int32_t nnz_total = a.rp[n];
   const int64_t gw = (int64_t)blockIdx.x * FU_WARPS + warp;
   const int64_t n_warps = (int64_t)gridDim.x * FU_WARPS;
@@ -475,10 +474,11 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
                           (const void*)pcg_fused_kernel<false, TmCfgGeneric, true>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, true>,
                           (const void*)pcg_fused_kernel<false, TmCfgBlock3, true>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, true>};
     int mn = 1 << 30;
-    for (const void* f : fns) {
+    for (int k = 0; k < 8; ++k) {
+      const size_t smem = tm_smem_bytes(FU_WARPS, (k & 2) ? TmCfgBlock3::CAP : TmCfgGeneric::CAP);
       int b = 0;
-      MYC_CUDA(ctx, cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
-      MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, f, FU_THREADS, FU_SMEM_BYTES));
+      MYC_CUDA(ctx, cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fns[k], FU_THREADS, smem));
       mn = b < mn ? b : mn;
     }
     max_blocks_per_sm = mn;
@@ -544,7 +544,8 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
                         (const void*)pcg_fused_kernel<false, TmCfgGeneric, true>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, true>,
                         (const void*)pcg_fused_kernel<false, TmCfgBlock3, true>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, true>};
   const void* fn = fns[vi];
-  MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FU_THREADS), params, FU_SMEM_BYTES, st));
+  MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FU_THREADS), params,
+                                            tm_smem_bytes(FU_WARPS, b3 ? TmCfgBlock3::CAP : TmCfgGeneric::CAP), st));
   ctx->launches++;
   *handled = 1;
   return MYC_OK;

@@ -36,18 +36,28 @@ struct TmCfgGeneric {
   static constexpr int CAP = 256;     // elements a stage window may hold (16*15 + alignment slack)
   static constexpr bool B3 = false;
 };
+#ifndef TM_B3_ROWS
+#define TM_B3_ROWS 18                 // 6 nodes per tile
+#endif
+#ifndef TM_B3_CAP
+#define TM_B3_CAP 288                 // 18*15 + alignment slack, multiple of 32
+#endif
 struct TmCfgBlock3 {
-  static constexpr int ROWS = 18;     // 6 nodes
-  static constexpr int CAP = 288;     // 18*15 + alignment slack, multiple of 32
+  static constexpr int ROWS = TM_B3_ROWS;
+  static constexpr int CAP = TM_B3_CAP;
   static constexpr bool B3 = true;
 };
+static_assert(TM_B3_ROWS % 3 == 0, "node-block tiles hold whole nodes");
 constexpr int TM_WARPS = 8;
 constexpr int TM_THREADS = 32 * TM_WARPS;
 constexpr int TM_STAGES = 2;
 constexpr int TM_BLOCKS_PER_SM = 4;                 // x TM_WARPS tile pipelines per SM
-constexpr int TM_MAX_CAP = 288;                     // stage stride in shared memory (largest Cfg::CAP)
-constexpr size_t TM_SMEM_PER_WARP = (size_t)TM_STAGES * TM_MAX_CAP * (sizeof(double) + sizeof(int32_t));
-constexpr size_t TM_SMEM_BYTES = TM_WARPS * TM_SMEM_PER_WARP + TM_WARPS * TM_STAGES * sizeof(uint64_t) + 128;
+// shared memory of one block of `warps` tile pipelines whose stages hold `cap` elements: the smaller
+// it is, the more of the 256 KB SM array is left to L1 for the x gathers
+__host__ __device__ constexpr size_t tm_smem_per_warp(int cap) { return (size_t)TM_STAGES * cap * (sizeof(double) + sizeof(int32_t)); }
+__host__ __device__ constexpr size_t tm_smem_bytes(int warps, int cap) {
+  return warps * tm_smem_per_warp(cap) + warps * TM_STAGES * sizeof(uint64_t) + 128;
+}
 
 __device__ __forceinline__ uint32_t tm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -94,11 +104,11 @@ struct TmPipe {
 };
 
 __device__ __forceinline__ void tm_pipe_init(TmPipe& pp, unsigned char* smem_base, int warps_per_block, int warp,
-                                             int lane) {
-  pp.s_val = reinterpret_cast<double*>(smem_base) + (size_t)warp * TM_STAGES * TM_MAX_CAP;
-  pp.s_col = reinterpret_cast<int32_t*>(smem_base + (size_t)warps_per_block * TM_STAGES * TM_MAX_CAP * sizeof(double)) +
-             (size_t)warp * TM_STAGES * TM_MAX_CAP;
-  pp.bars = reinterpret_cast<uint64_t*>(smem_base + (size_t)warps_per_block * TM_SMEM_PER_WARP) + warp * TM_STAGES;
+                                             int lane, int cap) {
+  pp.s_val = reinterpret_cast<double*>(smem_base) + (size_t)warp * TM_STAGES * cap;
+  pp.s_col = reinterpret_cast<int32_t*>(smem_base + (size_t)warps_per_block * TM_STAGES * cap * sizeof(double)) +
+             (size_t)warp * TM_STAGES * cap;
+  pp.bars = reinterpret_cast<uint64_t*>(smem_base + (size_t)warps_per_block * tm_smem_per_warp(cap)) + warp * TM_STAGES;
   pp.phase_bits = 0;
   pp.head_in_flight = false;
   // the matrix is read once per sweep: evict-first, keep L2 for the gathered vector
@@ -131,7 +141,7 @@ __device__ __forceinline__ void tm_warp_sweep(TmPipe& pp, int64_t n_rows, const 
                                               double (&acc)[Epi::NACC == 0 ? 1 : Epi::NACC], int64_t gw,
                                               int64_t n_warps, int lane, int32_t nnz_total) {
   static_assert(TM_STAGES == 2, "the sweep is written for a 2-stage ring");
-  static_assert(Cfg::ROWS <= 32 && Cfg::CAP <= TM_MAX_CAP && Cfg::CAP % 32 == 0, "tile shape");
+  static_assert(Cfg::ROWS <= 32 && Cfg::CAP % 32 == 0, "tile shape");
   constexpr int ROWS = Cfg::ROWS;
   // Tiles are dealt round-robin over all warps of the grid (tile = gw + j * n_warps): at any time
   // the whole chip works inside one moving window of ~n_warps*ROWS rows, so the x entries gathered
@@ -159,8 +169,8 @@ __device__ __forceinline__ void tm_warp_sweep(TmPipe& pp, int64_t n_rows, const 
     if (tm_tile_staged(lo, hi, nnz4, Cfg::CAP, a0, a1)) {
       const int32_t n = a1 - a0;
       tm_mbar_expect_tx(&bars[s], (uint32_t)n * 12u);
-      tm_bulk_load(s_val + (size_t)s * TM_MAX_CAP, v + a0, (uint32_t)n * 8u, &bars[s], pp.l2_stream);
-      tm_bulk_load(s_col + (size_t)s * TM_MAX_CAP, ci + a0, (uint32_t)n * 4u, &bars[s], pp.l2_stream);
+      tm_bulk_load(s_val + (size_t)s * Cfg::CAP, v + a0, (uint32_t)n * 8u, &bars[s], pp.l2_stream);
+      tm_bulk_load(s_col + (size_t)s * Cfg::CAP, ci + a0, (uint32_t)n * 4u, &bars[s], pp.l2_stream);
     }
   };
 
@@ -198,8 +208,8 @@ __device__ __forceinline__ void tm_warp_sweep(TmPipe& pp, int64_t n_rows, const 
       int32_t a0, a1;
       const bool staged_tile = tm_tile_staged(lo, hi, nnz4, Cfg::CAP, a0, a1);
       if (hi - a0 <= Cfg::CAP) {
-        double* sv = s_val + (size_t)s * TM_MAX_CAP;
-        int32_t* sc = s_col + (size_t)s * TM_MAX_CAP;
+        double* sv = s_val + (size_t)s * Cfg::CAP;
+        int32_t* sc = s_col + (size_t)s * Cfg::CAP;
         if (staged_tile) {
           tm_mbar_wait(&bars[s], (pp.phase_bits >> s) & 1u);
           pp.phase_bits ^= (1u << s);
@@ -329,7 +339,7 @@ myc_spmv_tma_kernel(int64_t n_rows, const int32_t* __restrict__ rp, const int32_
   if (done && *done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   TmPipe pp;
-  tm_pipe_init(pp, tm_smem, TM_WARPS, warp, lane);
+  tm_pipe_init(pp, tm_smem, TM_WARPS, warp, lane, Cfg::CAP);
   double acc[Epi::NACC == 0 ? 1 : Epi::NACC];
 #pragma unroll
   for (int j = 0; j < (Epi::NACC == 0 ? 1 : Epi::NACC); ++j) acc[j] = 0.0;
@@ -349,12 +359,12 @@ static inline int myc_launch_spmv_tma(myc_ctx* ctx, int64_t n_rows, const int32_
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
     MYC_CUDA(ctx, cudaFuncSetAttribute(myc_spmv_tma_kernel<Cfg, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)TM_SMEM_BYTES));
+                                       (int)tm_smem_bytes(TM_WARPS, Cfg::CAP)));
     attr_set = true;
   }
   const int64_t n_tiles = ceil_div64(n_rows, Cfg::ROWS);
   const int grid = grid_for(ctx, ceil_div64(n_tiles, TM_WARPS), TM_BLOCKS_PER_SM);
-  myc_spmv_tma_kernel<Cfg, Epi><<<grid, TM_THREADS, TM_SMEM_BYTES, st>>>(n_rows, rp, ci, v, x, epi, partials, counter,
+  myc_spmv_tma_kernel<Cfg, Epi><<<grid, TM_THREADS, tm_smem_bytes(TM_WARPS, Cfg::CAP), st>>>(n_rows, rp, ci, v, x, epi, partials, counter,
                                                                         out, done);
   MYC_LAUNCHED(ctx);
   return MYC_OK;
