@@ -463,3 +463,46 @@ def test_ramp_real_snapshot_cascade(golden_dir, monkeypatch):
     assert np.array_equal(got[:, 0], fd[:, 0])
     assert np.abs(got[:, 1] - fd[:, 1]).max() <= 1e-7 * np.abs(fd[:, 1]).max()
     print("real snapshot ramp: iterations per step", rec["iterations"][:6], "...")
+
+
+@pytest.mark.parametrize("case", ["X", "shear"])
+def test_other_load_cases_vs_oracle(case, monkeypatch):
+    """X and shear load cases (BASELINE configs 2 and 5; not in the reference, whose generic
+    solve_system is the oracle): BC sets bit-exact, U within 1e-8 of the direct solve."""
+    coords, n1, n2 = synth_network(96, seed=11)
+    axis, comp = fs.LOAD_CASES[case]
+    hi, lo = fs.grip_nodes(coords, 0.5, axis)
+    kd, kv = fs.build_bc(hi, lo, 0.02, -0.02, comp)
+    kdo, kvo = fo.build_bc(*fo.grip_nodes(coords, 0.5, axis), 0.02, -0.02, comp)
+    assert np.array_equal(kd, kdo) and np.array_equal(kv, kvo)
+    monkeypatch.setattr(fs, "PCG_RTOL", 1e-12)
+    mesh = dv.DeviceMesh.from_host(coords, n1, n2)
+    res = fs.analyze_load_case(mesh, kd, kv, react_dofs=3 * hi + comp)
+    Ko = fo.assemble_global_stiffness(coords, n1, n2, np.ones(len(n1), bool))
+    Uo = fo.solve_system(Ko, kdo, kvo)
+    U = res.U.cpu().numpy()
+    assert np.linalg.norm(U - Uo) <= U_RTOL * np.linalg.norm(Uo)
+    tf = (Ko @ Uo)[3 * hi + comp].sum()
+    assert abs(res.total_force - tf) <= 1e-7 * abs(tf)
+
+
+def test_snapshot_cli_with_binary_sidecar(tmp_path, monkeypatch):
+    """write_snapshot -> fea_solver(results_dir) reads the mesh.npz side-car and writes the
+    reference's output files; a second run from the CSVs alone gives identical records."""
+    from mycelium_fea_project_b200.synth import write_snapshot
+    coords, n1, n2 = synth_network(24, seed=3)
+    monkeypatch.setattr(fs, "N_STEPS", 4)
+    monkeypatch.setattr(fs, "GRIP_LENGTH", 0.3)
+    d1, d2 = tmp_path / "a", tmp_path / "b"
+    write_snapshot(str(d1), coords, n1, n2, binary_sidecar=True)
+    write_snapshot(str(d2), coords, n1, n2, binary_sidecar=False)
+    r1 = fs.fea_solver(str(d1), tol=fs.GRIP_LENGTH)
+    r2 = fs.fea_solver(str(d2), tol=fs.GRIP_LENGTH)
+    for f in ("stress_record.csv", "active_elements.csv", "node_displacements.csv", "force_displacement.csv",
+              "runtime.txt"):
+        assert os.path.isfile(d1 / "fea_results" / f) and os.path.isfile(d2 / "fea_results" / f)
+    # the CSV path parses coordinates like the reference (pandas default parser, <= 1 ulp off)
+    a, b = np.array(r1["disp"]), np.array(r2["disp"])
+    assert a.shape == b.shape and np.abs(a - b).max() <= 1e-9 * np.abs(a).max()
+    df = pd.read_csv(d1 / "fea_results" / "node_displacements.csv")
+    assert list(df.columns[:3]) == ["0", "1", "2"] and df.columns[-1] == "step" and len(df) == 4

@@ -1,0 +1,31 @@
+"""CPU tests of host-side I/O helpers (no GPU compute)."""
+import numpy as np
+
+from mycelium_fea_project_b200.synth import synth_network, write_snapshot
+
+
+def test_snapshot_roundtrip_csv_and_sidecar(tmp_path):
+    from mycelium_fea_project_b200 import fea_solver as fs
+    coords, n1, n2 = synth_network(32, 20, seed=9)
+    write_snapshot(str(tmp_path / "s"), coords, n1, n2, binary_sidecar=True)
+    c, a, b = fs.load_snapshot(str(tmp_path / "s"))            # prefers mesh.npz
+    assert np.array_equal(c, coords) and np.array_equal(a, n1) and np.array_equal(b, n2)
+    write_snapshot(str(tmp_path / "t"), coords, n1, n2, binary_sidecar=False)
+    c, a, b = fs.load_snapshot(str(tmp_path / "t"))            # reference CSV schema, parsed like the reference
+    # (pandas' default float parser, which the reference uses too, is not round-trip exact: <= 1 ulp)
+    assert np.allclose(c, coords, rtol=4e-16, atol=0) and np.array_equal(a, n1) and np.array_equal(b, n2)
+    import pandas as pd
+    nodes = pd.read_csv(tmp_path / "t" / "nodes.csv")
+    elems = pd.read_csv(tmp_path / "t" / "elements.csv")
+    assert list(nodes.columns) == ["node_id", "x", "y", "z"] and list(elems.columns) == ["elem_id", "n1", "n2"]
+    assert np.array_equal(nodes["node_id"].values, np.arange(len(coords)))
+
+
+def test_generator_is_seeded_and_matches_survey_counts():
+    c1, a1, b1 = synth_network(64)
+    c2, a2, b2 = synth_network(64)
+    assert np.array_equal(c1, c2) and np.array_equal(a1, a2) and np.array_equal(b1, b2)
+    assert (len(c1), len(a1)) == (2743, 3609)                 # SURVEY.md section 6 / BASELINE.md
+    assert np.all(a1 < b1) and c1[:, 2].max() == 0.0
+    c3, _, _ = synth_network(64, seed=1)
+    assert len(c3) != len(c1) or not np.array_equal(c3, c1)
