@@ -148,3 +148,20 @@ def test_live_reference_matches_oracle(tmp_path):
                                os.path.join(src, "fea_results", f), shallow=False)
     finally:
         shutil.rmtree(out)
+
+
+def test_petsc_style_c_port_agrees_with_direct_solve(golden_dir):
+    """oracle/pcg_port.c (the multi-threaded restatement of the reference's PETSc path used as a CPU
+    baseline) solves the same system: MatZeroRowsColumns-style elimination + Jacobi-PCG."""
+    from oracle import pcg_port
+    if not pcg_port.available():
+        pytest.skip("oracle/_build/libpcg_port.so not built (run __graft_entry__.build())")
+    g = np.load(os.path.join(golden_dir, "solve_synth64.npz"))
+    c, n1, n2 = synth_network(64)
+    K = fo.assemble_global_stiffness(c, n1, n2, np.ones(len(n1), bool))
+    U, it, rel = pcg_port.solve_system_petsc_style(K, g["known_dofs"], g["known_vals"], rtol=1e-14, max_iters=100000)
+    assert it < 100000 and rel <= 1e-14
+    assert np.array_equal(U[g["known_dofs"]], g["known_vals"]) or np.allclose(U[g["known_dofs"]], g["known_vals"], rtol=1e-11)
+    # PETSc's residual is relative to a b that contains the prescribed values, so the free part is
+    # resolved less tightly than rtol suggests
+    assert np.linalg.norm(U - g["U"]) <= 1e-6 * np.linalg.norm(g["U"])
