@@ -32,6 +32,8 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
     ctx->no_fused_pcg = f && f[0] == '1';
     const char* g = getenv("MYC_NO_BLOCK3_SPMV");
     ctx->no_block3_spmv = g && g[0] == '1';
+    const char* y = getenv("MYC_NO_SYM3");
+    ctx->no_sym3 = y && y[0] == '1';
   }
   e = cudaSetDevice(device_ordinal);
   cudaDeviceProp prop;
@@ -61,7 +63,8 @@ extern "C" int myc_destroy(myc_ctx* ctx) {
   myc_dist_destroy(ctx);
   DevBuf* all[] = {&ctx->scan_tmp, &ctx->sort_keys[0], &ctx->sort_keys[1], &ctx->sort_vals[0], &ctx->sort_vals[1],
                    &ctx->sort_table, &ctx->edge_cnt, &ctx->node_deg, &ctx->node_bc, &ctx->partials, &ctx->scalars,
-                   &ctx->vec[0], &ctx->vec[1], &ctx->vec[2], &ctx->vec[3], &ctx->vec[4], &ctx->vec[5], &ctx->misc};
+                   &ctx->vec[0], &ctx->vec[1], &ctx->vec[2], &ctx->vec[3], &ctx->vec[4], &ctx->vec[5], &ctx->misc,
+                   &ctx->sym_val, &ctx->sym_col};
   for (DevBuf* b : all) if (b->p) cudaFree(b->p);
   for (DevBuf& b : ctx->lc) if (b.p) cudaFree(b.p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -30,6 +30,7 @@ struct myc_ctx {
   bool force_plain_spmv = false;   // MYC_FORCE_PLAIN_SPMV=1: use the non-TMA CSR-stream kernel
   bool no_fused_pcg = false;       // MYC_NO_FUSED_PCG=1: always use the multi-kernel PCG
   bool no_block3_spmv = false;     // MYC_NO_BLOCK3_SPMV=1: ignore the node-block hint
+  bool no_sym3 = false;            // MYC_NO_SYM3=1: the fused PCG streams the CSR, not the symmetric block view
   bool csr_block3 = false;         // caller's hint: the CSR it passes has the 3x3 node-block structure
 
   // ---- scratch arenas (grown on demand, never shrunk)
@@ -45,6 +46,7 @@ struct myc_ctx {
   DevBuf vec[6];                // PCG work vectors (r, p(global), Ap, ...)
   DevBuf misc;                  // small temporaries (flags, gather-sum output ...)
   DevBuf lc[14];                // device copies owned by myc_load_case_host
+  DevBuf sym_val, sym_col;      // symmetric 3x3 block view of K for the fused PCG (spmv_sym3.cuh)
   void* h_pinned = nullptr;     // 4 KB pinned staging for host scalars
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
@@ -54,6 +56,7 @@ struct myc_ctx {
   cudaEvent_t prof_ev[2 * PROF_PAIRS] = {nullptr};
   double prof_ms = 0.0, prof_bytes = 0.0;
   int64_t prof_samples = 0, prof_launches = 0;
+  int prof_op = 0;               // operator the last profiled fused solve streamed (0/1 CSR, 2 sym3)
 
   // ---- assembly plan retained between symbolic and numeric
   bool plan_valid = false;

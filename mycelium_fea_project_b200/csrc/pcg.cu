@@ -24,7 +24,7 @@ int myc_dist_halo(myc_ctx* ctx, double* d_x_global, cudaStream_t st);           
 int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
                       const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
                       const double* d_dinv, const double* d_binv, double reg, int64_t maxit, double* d_x,
-                      cudaStream_t st, int* handled);                               // pcg_fused.cu
+                      cudaStream_t st, int* handled, int* op_used);                 // pcg_fused.cu
 
 namespace {
 
@@ -296,10 +296,10 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   // ---- the whole iteration loop is one persistent cooperative kernel per GPU (NVLink peer
   // memory between GPUs); falls through to the multi-kernel / NCCL loop when not applicable
   {
-    int handled = 0;
+    int handled = 0, op_used = 0;
     if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
     MYC_TRY(myc_pcg_fused_try(ctx, n_rows, n_cols_global, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv,
-                              block3 ? d_binv : nullptr, reg, maxit, d_x, st, &handled));
+                              block3 ? d_binv : nullptr, reg, maxit, d_x, st, &handled, &op_used));
     if (handled) {
       if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
       MYC_CUDA(ctx, cudaMemcpyAsync(h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
@@ -321,8 +321,11 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
         ctx->prof_ms += ms;
         ctx->prof_samples += 1;
         ctx->prof_launches += 1;
-        ctx->prof_bytes += ((double)fin.iters + 1.0) * (12.0 * h_nnz + 20.0 * (double)n_rows) +
+        // bytes the sweep streams per iteration: CSR 12 B/nnz, symmetric block view 52 B per 9 nnz
+        const double mat = op_used == 2 ? (52.0 / 9.0) * h_nnz : 12.0 * h_nnz;
+        ctx->prof_bytes += ((double)fin.iters + 1.0) * (mat + 20.0 * (double)n_rows) +
                            (double)fin.iters * 96.0 * (double)n_rows;
+        ctx->prof_op = op_used;
       }
       if (h_out_iters) *h_out_iters = (int64_t)fin.iters;
       if (h_out_relres) *h_out_relres = rel;

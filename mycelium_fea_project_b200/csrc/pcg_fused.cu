@@ -32,6 +32,9 @@
 #include "common.cuh"
 #include "spmv.cuh"
 #include "spmv_tma.cuh"
+#include "spmv_sym3.cuh"
+
+#include <type_traits>
 
 namespace {
 
@@ -49,6 +52,9 @@ struct FusedArgs {
   const int32_t* rp;
   const int32_t* ci;
   const double* v;
+  const double* bval;      // symmetric 3x3 node-block view of K (spmv_sym3.cuh), or null
+  const int32_t* bcol;
+  int32_t nb_total;
   const double* dinv;
   const double* binv;      // (n_rows/3, 9) block-Jacobi inverse, or null for point Jacobi
   double* x;
@@ -177,8 +183,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define FT_MARK(k) do { } while (0)
 #endif
 
-template <bool BLOCK3, class Cfg, bool DIST>
+// OP: 0 = generic CSR sweep, 1 = node-block CSR sweep, 2 = symmetric 3x3 block operator
+template <bool BLOCK3, int OP, bool DIST>
 __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
+  using Cfg = std::conditional_t<OP == 1, TmCfgBlock3, TmCfgGeneric>;
+  using Pipe = std::conditional_t<OP == 2, TmSymPipe, TmPipe>;
   extern __shared__ __align__(128) unsigned char fu_smem[];
   __shared__ double s_red[FU_WARPS][3];
   __shared__ double s_tot[3];
@@ -193,8 +202,9 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   double* const u = a.peer_u[a.rank];
   PeerSync* const my_sync = a.peer_sync[a.rank];
 
-  TmPipe pp;
-  tm_pipe_init(pp, fu_smem, FU_WARPS, warp, lane, Cfg::CAP);
+  Pipe pp;
+  if constexpr (OP == 2) tm_sym_pipe_init(pp, fu_smem, FU_WARPS, warp, lane);
+  else tm_pipe_init(pp, fu_smem, FU_WARPS, warp, lane, Cfg::CAP);
   const int32_t nnz_total = a.rp[n];
   const int64_t gw = (int64_t)blockIdx.x * FU_WARPS + warp;
   const int64_t n_warps = (int64_t)gridDim.x * FU_WARPS;
@@ -273,7 +283,10 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   for (;;) {
     // ---- phase A: w = A u, partial dots
     double acc[3] = {0.0, 0.0, 0.0};
-    tm_warp_sweep<Cfg, EpiFused, true, true>(pp, n, a.rp, a.ci, a.v, u, epi, acc, gw, n_warps, lane, nnz_total);
+    if constexpr (OP == 2)
+      tm_sym3_sweep<EpiFused, true>(pp, n, a.rp, a.bval, a.bcol, u, epi, acc, gw, n_warps, lane, a.nb_total);
+    else
+      tm_warp_sweep<Cfg, EpiFused, true, true>(pp, n, a.rp, a.ci, a.v, u, epi, acc, gw, n_warps, lane, nnz_total);
     FT_MARK(0);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -385,7 +398,8 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     FT_MARK(3);
   }
   // no bulk copy may be in flight when the block exits
-  tm_pipe_drain<Cfg>(pp, n, a.rp, gw, nnz_total);
+  if constexpr (OP == 2) tm_sym_pipe_drain(pp, n, a.rp, gw, a.nb_total);
+  else tm_pipe_drain<Cfg>(pp, n, a.rp, gw, nnz_total);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.sc->iters = it;
     a.sc->rr_final = rr;
@@ -456,11 +470,28 @@ extern "C" int myc_dist_peer_open(myc_ctx* ctx, const uint8_t* h_handles) {
 
 // Returns MYC_OK and fills *handled = 1 if the fused path ran; *handled = 0 means "not applicable
 // here" (caller falls back to the multi-kernel PCG).  On entry r = b - A x0 is in ctx->vec[1] and
-// sc->tol2 is set (pcg.cu does that for both paths).
+// sc->tol2 is set (pcg.cu does that for both paths).  *op_used: 0 generic CSR, 1 node-block CSR,
+// 2 symmetric 3x3 block view.
+namespace {
+template <bool B3PC, int OP, bool DIST>
+const void* fused_fn() { return (const void*)pcg_fused_kernel<B3PC, OP, DIST>; }
+// index = dist*6 + op*2 + block3pc
+const void* fused_variant(int idx) {
+  static const void* tab[12] = {
+      fused_fn<false, 0, false>(), fused_fn<true, 0, false>(), fused_fn<false, 1, false>(), fused_fn<true, 1, false>(),
+      fused_fn<false, 2, false>(), fused_fn<true, 2, false>(), fused_fn<false, 0, true>(),  fused_fn<true, 0, true>(),
+      fused_fn<false, 1, true>(),  fused_fn<true, 1, true>(),  fused_fn<false, 2, true>(),  fused_fn<true, 2, true>()};
+  return tab[idx];
+}
+size_t fused_smem(int op) {
+  return op == 2 ? tm_sym_smem_bytes(FU_WARPS) : tm_smem_bytes(FU_WARPS, op == 1 ? TmCfgBlock3::CAP : TmCfgGeneric::CAP);
+}
+}  // namespace
+
 int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
                       const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
                       const double* d_dinv, const double* d_binv, double reg, int64_t maxit, double* d_x,
-                      cudaStream_t st, int* handled) {
+                      cudaStream_t st, int* handled, int* op_used) {
   *handled = 0;
   if (ctx->no_fused_pcg) return MYC_OK;
   const bool dist = ctx->world > 1;
@@ -469,16 +500,12 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;   // (same allocator on every rank)
   static int max_blocks_per_sm = -1;
   if (max_blocks_per_sm < 0) {
-    const void* fns[8] = {(const void*)pcg_fused_kernel<false, TmCfgGeneric, false>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, false>,
-                          (const void*)pcg_fused_kernel<false, TmCfgBlock3, false>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, false>,
-                          (const void*)pcg_fused_kernel<false, TmCfgGeneric, true>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, true>,
-                          (const void*)pcg_fused_kernel<false, TmCfgBlock3, true>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, true>};
     int mn = 1 << 30;
-    for (int k = 0; k < 8; ++k) {
-      const size_t smem = tm_smem_bytes(FU_WARPS, (k & 2) ? TmCfgBlock3::CAP : TmCfgGeneric::CAP);
+    for (int k = 0; k < 12; ++k) {
+      const size_t smem = fused_smem((k % 6) / 2);
       int b = 0;
-      MYC_CUDA(ctx, cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fns[k], FU_THREADS, smem));
+      MYC_CUDA(ctx, cudaFuncSetAttribute(fused_variant(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fused_variant(k), FU_THREADS, smem));
       mn = b < mn ? b : mn;
     }
     max_blocks_per_sm = mn;
@@ -493,8 +520,30 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   MYC_TRY(myc_ensure(ctx, ctx->vec[5], (size_t)(n_rows + 1) * sizeof(double)));
   MYC_TRY(myc_ensure(ctx, ctx->misc, 512));
   MYC_TRY(myc_ensure(ctx, ctx->partials, (size_t)ctx->sm_count * 16 * 4 * sizeof(double)));
+  // ---- operator: node-block structured K -> symmetric 3x3 block view (52 B instead of 108 B per block)
   const bool b3 = ctx->csr_block3 && n_rows % 3 == 0 && !ctx->no_block3_spmv;
-  const int64_t n_tiles = ceil_div64(n_rows, b3 ? TmCfgBlock3::ROWS : TmCfgGeneric::ROWS);
+  int op = b3 ? 1 : 0;
+  int32_t nb_total = 0;
+  if (b3 && !ctx->no_sym3 && n_rows > 0) {
+    int32_t h_nnz = 0;
+    MYC_CUDA(ctx, cudaMemcpyAsync(&h_nnz, d_row_ptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaStreamSynchronize(st));
+    nb_total = h_nnz / 9;
+    MYC_TRY(myc_ensure(ctx, ctx->sym_val, ((size_t)nb_total + 4) * 6 * sizeof(double)));
+    MYC_TRY(myc_ensure(ctx, ctx->sym_col, ((size_t)nb_total + 4) * sizeof(int32_t)));
+    int* bad = (int*)((char*)ctx->misc.p + 320);
+    MYC_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(int), st));
+    myc_sym3_convert_kernel<<<grid_for(ctx, ceil_div64(n_rows / 3, 256), 8), 256, 0, st>>>(
+        n_rows / 3, d_row_ptr, d_col_idx, d_val, (double*)ctx->sym_val.p, (int32_t*)ctx->sym_col.p, bad);
+    MYC_LAUNCHED(ctx);
+    int* h = (int*)ctx->h_pinned;
+    MYC_CUDA(ctx, cudaMemcpyAsync(h, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (*h == 0) op = 2;       // every block bitwise symmetric: the solver streams the compact view
+  }
+  if (op_used) *op_used = op;
+  const int64_t n_tiles = op == 2 ? ceil_div64(n_rows / 3, TmCfgSym::NODES)
+                                  : ceil_div64(n_rows, op == 1 ? TmCfgBlock3::ROWS : TmCfgGeneric::ROWS);
   int grid = ctx->sm_count;
   if (ceil_div64(n_tiles, FU_WARPS) < grid) grid = (int)ceil_div64(n_tiles, FU_WARPS);
   if (grid < 1) grid = 1;
@@ -508,6 +557,9 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   a.rp = d_row_ptr;
   a.ci = d_col_idx;
   a.v = d_val;
+  a.bval = op == 2 ? (const double*)ctx->sym_val.p : nullptr;
+  a.bcol = op == 2 ? (const int32_t*)ctx->sym_col.p : nullptr;
+  a.nb_total = nb_total;
   a.dinv = d_dinv;
   a.binv = d_binv;
   a.x = d_x;
@@ -538,14 +590,8 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
     a.peer_sync[0] = nullptr;
   }
   void* params[] = {&a};
-  const int vi = (dist ? 4 : 0) + (b3 ? 2 : 0) + (d_binv ? 1 : 0);
-  const void* fns[8] = {(const void*)pcg_fused_kernel<false, TmCfgGeneric, false>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, false>,
-                        (const void*)pcg_fused_kernel<false, TmCfgBlock3, false>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, false>,
-                        (const void*)pcg_fused_kernel<false, TmCfgGeneric, true>, (const void*)pcg_fused_kernel<true, TmCfgGeneric, true>,
-                        (const void*)pcg_fused_kernel<false, TmCfgBlock3, true>, (const void*)pcg_fused_kernel<true, TmCfgBlock3, true>};
-  const void* fn = fns[vi];
-  MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FU_THREADS), params,
-                                            tm_smem_bytes(FU_WARPS, b3 ? TmCfgBlock3::CAP : TmCfgGeneric::CAP), st));
+  const void* fn = fused_variant((dist ? 6 : 0) + op * 2 + (d_binv ? 1 : 0));
+  MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FU_THREADS), params, fused_smem(op), st));
   ctx->launches++;
   *handled = 1;
   return MYC_OK;
