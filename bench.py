@@ -344,8 +344,9 @@ def run_ours(args):
     if spmv_n:
         ach = spmv_bytes / (spmv_ms * 1e-3) / 1e9
         fused = world == 1 and args.precond == "jacobi" and os.environ.get("MYC_NO_FUSED_PCG") != "1"
-        kname = ("pcg_fused_kernel (one persistent launch per solve: TMA SpMV sweep + fused dots + vector "
-                 "recurrences per iteration; bytes = (its+1)*(12 nnz + 20 n) + its*96 n)") if fused else \
+        kname = ("pcg_fused_kernel (one persistent launch per solve: TMA sweep over the symmetric 3x3 block view of "
+                 "K + fused dots + vector recurrences per iteration; bytes = (its+1)*(52/9 nnz + 20 n) + its*96 n, "
+                 "i.e. what this kernel has to stream -- 12 nnz instead of 52/9 nnz if MYC_NO_SYM3=1)") if fused else \
             "myc_spmv_tma_kernel<EpiCgAp> (Ap = K p + reg p, fused p.Ap; every 32nd launch sampled)"
         roof = {"bound": "hbm", "kernel": kname,
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
