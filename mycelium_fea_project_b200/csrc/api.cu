@@ -34,6 +34,8 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
     ctx->no_block3_spmv = g && g[0] == '1';
     const char* y = getenv("MYC_NO_SYM3");
     ctx->no_sym3 = y && y[0] == '1';
+    const char* z = getenv("MYC_NO_HALO_OVERLAP");
+    ctx->no_halo_overlap = z && z[0] == '1';
   }
   e = cudaSetDevice(device_ordinal);
   cudaDeviceProp prop;

@@ -74,6 +74,8 @@ struct FusedArgs {
   PeerSync* peer_sync[MYC_MAX_WORLD];
   int64_t give_lo[MYC_MAX_WORLD], give_hi[MYC_MAX_WORLD];   // DOF ranges of MY rows that peer q gathers
   unsigned char recv_any[MYC_MAX_WORLD];       // I gather rows of peer q
+  unsigned recv_mask;                          // the same as a bit mask
+  int halo_overlap;                            // gated sweep: halo waits move from barrier #2 into the sweep
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
@@ -234,7 +236,8 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
         if (ln < a.world && ln != a.rank) {
           __threadfence_system();
           if (a.give_hi[ln] > a.give_lo[ln]) st_relaxed_sys(&a.peer_sync[ln]->flag_halo[a.rank], e);
-          if (a.recv_any[ln]) {
+          // with the gated sweep (OP == 2) only the warps that gather halo entries wait for them
+          if (!(OP == 2 && a.halo_overlap) && a.recv_any[ln]) {
             unsigned spins = 0;
             while (ld_acquire_sys(&my_sync->flag_halo[ln]) < e)
               if (++spins > FU_SPIN_LIMIT) __trap();
@@ -283,8 +286,24 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   for (;;) {
     // ---- phase A: w = A u, partial dots
     double acc[3] = {0.0, 0.0, 0.0};
-    if constexpr (OP == 2)
-      tm_sym3_sweep<EpiFused, true>(pp, n, a.rp, a.bval, a.bcol, u, epi, acc, gw, n_warps, lane, a.nb_total);
+    if constexpr (OP == 2) {
+      if constexpr (DIST) {
+        if (a.halo_overlap) {
+          TmHaloGate gate;
+          gate.own_lo = a.row_offset;
+          gate.own_hi = a.row_offset + n;
+          gate.flags = my_sync->flag_halo;
+          gate.epoch = ep_halo;
+          gate.world = a.world;
+          gate.recv_mask = a.recv_mask;
+          tm_sym3_sweep<EpiFused, true, true>(pp, n, a.rp, a.bval, a.bcol, u, epi, acc, gw, n_warps, lane, a.nb_total, gate);
+        } else {
+          tm_sym3_sweep<EpiFused, true, false>(pp, n, a.rp, a.bval, a.bcol, u, epi, acc, gw, n_warps, lane, a.nb_total, TmHaloGate{});
+        }
+      } else {
+        tm_sym3_sweep<EpiFused, true, false>(pp, n, a.rp, a.bval, a.bcol, u, epi, acc, gw, n_warps, lane, a.nb_total, TmHaloGate{});
+      }
+    }
     else
       tm_warp_sweep<Cfg, EpiFused, true, true>(pp, n, a.rp, a.ci, a.v, u, epi, acc, gw, n_warps, lane, nnz_total);
     FT_MARK(0);
@@ -398,7 +417,10 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     FT_MARK(3);
   }
   // no bulk copy may be in flight when the block exits
-  if constexpr (OP == 2) tm_sym_pipe_drain(pp, n, a.rp, gw, a.nb_total);
+  if constexpr (OP == 2) {
+    if (DIST && a.halo_overlap) tm_sym_pipe_drain<true>(pp, n, a.rp, gw, n_warps, a.nb_total);
+    else tm_sym_pipe_drain<false>(pp, n, a.rp, gw, n_warps, a.nb_total);
+  }
   else tm_pipe_drain<Cfg>(pp, n, a.rp, gw, nnz_total);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.sc->iters = it;
@@ -584,7 +606,9 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
       a.give_lo[q] = q == ctx->rank ? 0 : ctx->send_to[q].lo;
       a.give_hi[q] = q == ctx->rank ? 0 : ctx->send_to[q].hi;
       a.recv_any[q] = (q != ctx->rank && ctx->recv_from[q].hi > ctx->recv_from[q].lo) ? 1 : 0;
+      if (a.recv_any[q]) a.recv_mask |= 1u << q;
     }
+    a.halo_overlap = ctx->no_halo_overlap ? 0 : 1;
   } else {
     a.peer_u[0] = (double*)ctx->vec[0].p;
     a.peer_sync[0] = nullptr;

@@ -86,18 +86,42 @@ __device__ __forceinline__ void tm_sym_pipe_init(TmSymPipe& pp, unsigned char* s
   __syncwarp();
 }
 
+// Multi-GPU gate: entries of x outside [own_lo, own_hi) are stored by peer GPUs (halo).  Instead of
+// stalling every block at the barrier until the neighbours' halo flags arrive, only a warp whose
+// tile actually gathers remote entries waits for them -- and the sweep visits its first round of
+// tiles (which holds the low-boundary tiles) last, so the NVLink latency hides behind interior work.
+// Remote entries are read with ld.global.cg: an L1 line that straddles the own/halo boundary may have
+// been fetched (for an own entry) before the neighbour's store landed.
+struct TmHaloGate {
+  int64_t own_lo, own_hi;
+  const unsigned* flags;       // this rank's PeerSync.flag_halo[], written by the peers
+  unsigned epoch;
+  int world;
+  unsigned recv_mask;          // bit q: this rank gathers rows of peer q
+};
+__device__ __forceinline__ double tm_ld_cg(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned tm_ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // block offset of local node `nd` (clamped): the scalar CSR row pointer of its first row / 9
 __device__ __forceinline__ int32_t tm_sym_node_ptr(const int32_t* __restrict__ rp, int64_t nd, int64_t n_nodes) {
   return rp[3 * (nd < n_nodes ? nd : n_nodes)] / 9;
 }
 
 // One sweep of warp gw over its tiles.  x is gathered coherently (persistent solver kernel).
-template <class Epi, bool PREFETCH_NEXT>
+template <class Epi, bool PREFETCH_NEXT, bool GATED>
 __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, const int32_t* __restrict__ rp,
                                               const double* __restrict__ bval, const int32_t* __restrict__ bcol,
                                               const double* x, const Epi& epi,
                                               double (&acc)[Epi::NACC == 0 ? 1 : Epi::NACC], int64_t gw,
-                                              int64_t n_warps, int lane, int32_t nb_total) {
+                                              int64_t n_warps, int lane, int32_t nb_total, const TmHaloGate& gate) {
   constexpr int NODES = TmCfgSym::NODES, ROWS = TmCfgSym::ROWS, CAPB = TmCfgSym::CAPB;
   const int64_t n_nodes = n_rows / 3;
   const int64_t n_tiles = (n_nodes + NODES - 1) / NODES;
@@ -106,6 +130,10 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
   double* const s_val = pp.s_val;
   int32_t* const s_col = pp.s_col;
   uint64_t* const bars = pp.bars;
+  // visiting order: round (j + rot) % t_count; with the gate the first round comes last
+  const int64_t rot = (GATED && t_count > 1) ? 1 : 0;
+  auto tile_of = [&](int64_t j) -> int64_t { return gw + ((j + rot) % t_count) * n_warps; };
+  bool halo_ready = false;
 
   // lane l < NODES holds the block range [lo_l, hi_l) of node NODES*t + l
   auto load_np = [&](int64_t t, int32_t& lo_l, int32_t& hi_l) {
@@ -125,8 +153,8 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
 
   int32_t cur_lo = 0, cur_hi = 0, nxt_lo = 0, nxt_hi = 0, head_lo = 0, head_hi = 0;
   if (t_count > 0) {
-    load_np(gw, cur_lo, cur_hi);
-    if (t_count > 1) load_np(gw + n_warps, nxt_lo, nxt_hi);
+    load_np(tile_of(0), cur_lo, cur_hi);
+    if (t_count > 1) load_np(tile_of(1), nxt_lo, nxt_hi);
     head_lo = __shfl_sync(0xffffffffu, cur_lo, 0);
     head_hi = __shfl_sync(0xffffffffu, cur_hi, NODES - 1);
     if (!pp.head_in_flight && lane == 0) issue(0, head_lo, head_hi);
@@ -134,14 +162,14 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
 
   for (int64_t j = 0; j < t_count; ++j) {
     const int s = (int)(j % TM_STAGES);
-    const int64_t t = gw + j * n_warps;
+    const int64_t t = tile_of(j);
     const int64_t r0 = t * ROWS;
     if (j + 1 < t_count) {
       const int32_t lo1 = __shfl_sync(0xffffffffu, nxt_lo, 0), hi1 = __shfl_sync(0xffffffffu, nxt_hi, NODES - 1);
       if (lane == 0) issue((int)((j + 1) % TM_STAGES), lo1, hi1);
     }
     int32_t nn_lo = 0, nn_hi = 0;
-    if (j + 2 < t_count) load_np(t + 2 * n_warps, nn_lo, nn_hi);
+    if (j + 2 < t_count) load_np(tile_of(j + 2), nn_lo, nn_hi);
     const int32_t lo = __shfl_sync(0xffffffffu, cur_lo, 0);
     const int32_t hi = __shfl_sync(0xffffffffu, cur_hi, NODES - 1);
     // row (lane) -> its node's block range
@@ -176,9 +204,25 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
 #pragma unroll
         for (int u = 0; u < CAPB / 32; ++u) {
           const int k = first + lane + 32 * u;
+          const int32_t c = k < last ? sc[k] : 0;
+          bool remote = false;
+          if constexpr (GATED) {
+            remote = k < last && ((int64_t)c < gate.own_lo || (int64_t)c >= gate.own_hi);
+            if (!halo_ready && __any_sync(0xffffffffu, remote)) {
+              // this tile gathers halo entries: make sure the neighbours' stores have landed
+              if (lane < gate.world && ((gate.recv_mask >> lane) & 1u)) {
+                unsigned spins = 0;
+                while (tm_ld_acquire_sys(&gate.flags[lane]) < gate.epoch)
+                  if (++spins > (1u << 28)) __trap();
+              }
+              __syncwarp();
+              halo_ready = true;
+            }
+          }
           if (k < last) {
-            const int32_t c = sc[k];
-            const double x0 = x[c], x1 = x[c + 1], x2 = x[c + 2];
+            double x0, x1, x2;
+            if (GATED && remote) { x0 = tm_ld_cg(x + c); x1 = tm_ld_cg(x + c + 1); x2 = tm_ld_cg(x + c + 2); }
+            else { x0 = x[c]; x1 = x[c + 1]; x2 = x[c + 2]; }
             double2* b2 = reinterpret_cast<double2*>(sv + 6 * k);
             const double2 v01 = b2[0], v23 = b2[1], v45 = b2[2];        // xx xy | xz yy | yz zz
             const double p0 = fma(v23.x, x2, fma(v01.y, x1, v01.x * x0));
@@ -197,10 +241,20 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
         __syncwarp();
       } else if (row_ok) {
         // oversize tile (a node with very many neighbours): straight from global memory
+        if constexpr (GATED) {
+          if (!halo_ready) {     // rare path: wait unconditionally
+            if (lane < gate.world && ((gate.recv_mask >> lane) & 1u)) {
+              unsigned spins = 0;
+              while (tm_ld_acquire_sys(&gate.flags[lane]) < gate.epoch)
+                if (++spins > (1u << 28)) __trap();
+            }
+            halo_ready = true;
+          }
+        }
         for (int32_t b = my_lo; b < my_hi; ++b) {
           const double* m = bval + 6 * (size_t)b;
           const int32_t c = bcol[b];
-          const double x0 = x[c], x1 = x[c + 1], x2 = x[c + 2];
+          const double x0 = tm_ld_cg(x + c), x1 = tm_ld_cg(x + c + 1), x2 = tm_ld_cg(x + c + 2);
           const double p = comp == 0 ? fma(m[2], x2, fma(m[1], x1, m[0] * x0))
                          : comp == 1 ? fma(m[4], x2, fma(m[3], x1, m[1] * x0))
                                      : fma(m[5], x2, fma(m[4], x1, m[2] * x0));
@@ -222,14 +276,17 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
   }
 }
 
+template <bool GATED>
 __device__ __forceinline__ void tm_sym_pipe_drain(TmSymPipe& pp, int64_t n_rows, const int32_t* rp, int64_t gw,
-                                                  int32_t nb_total) {
+                                                  int64_t n_warps, int32_t nb_total) {
   if (!pp.head_in_flight) return;
   const int64_t n_nodes = n_rows / 3;
   const int64_t n_tiles = (n_nodes + TmCfgSym::NODES - 1) / TmCfgSym::NODES;
   if (gw < n_tiles) {
-    const int32_t lo = tm_sym_node_ptr(rp, gw * TmCfgSym::NODES, n_nodes);
-    const int32_t hi = tm_sym_node_ptr(rp, gw * TmCfgSym::NODES + TmCfgSym::NODES, n_nodes);
+    const int64_t t_count = (n_tiles - gw + n_warps - 1) / n_warps;
+    const int64_t t0 = gw + ((GATED && t_count > 1) ? 1 : 0) * n_warps;     // first tile the sweep visits
+    const int32_t lo = tm_sym_node_ptr(rp, t0 * TmCfgSym::NODES, n_nodes);
+    const int32_t hi = tm_sym_node_ptr(rp, t0 * TmCfgSym::NODES + TmCfgSym::NODES, n_nodes);
     int32_t a0, a1;
     if (tm_tile_staged(lo, hi, nb_total & ~3, TmCfgSym::CAPB, a0, a1)) tm_mbar_wait(&pp.bars[0], pp.phase_bits & 1u);
   }
