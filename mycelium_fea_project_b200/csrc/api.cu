@@ -34,8 +34,11 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
     ctx->no_block3_spmv = g && g[0] == '1';
     const char* y = getenv("MYC_NO_SYM3");
     ctx->no_sym3 = y && y[0] == '1';
-    const char* z = getenv("MYC_NO_HALO_OVERLAP");
-    ctx->no_halo_overlap = z && z[0] == '1';
+    // measured on 2 GPUs (512^2 per GPU): 37.3 us/iteration with the gated sweep against 35.4 us with
+    // the plain halo barrier -- the all-rank reduction barrier that follows absorbs the wait either
+    // way -- so the gate is opt-in
+    const char* z = getenv("MYC_HALO_OVERLAP");
+    ctx->no_halo_overlap = !(z && z[0] == '1');
   }
   e = cudaSetDevice(device_ordinal);
   cudaDeviceProp prop;
