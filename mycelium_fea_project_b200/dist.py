@@ -159,6 +159,9 @@ class DistributedSolver:
                                                 self.world))
             self.ctx.rank, self.ctx.world = self.rank, self.world
         self._install_plan()
+        # NVLink peer buffers now, not inside the first solve: opening 7 IPC handles (peer access is
+        # enabled lazily per peer) takes seconds on an 8-GPU board
+        self._ensure_peer(3 * self.n_nodes)
 
     def _install_plan(self):
         """Make this solver's partition the one the C library's collectives use (several solvers,
