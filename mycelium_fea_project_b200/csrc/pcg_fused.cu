@@ -149,8 +149,15 @@ __device__ __forceinline__ void local_barrier(const FusedArgs& a, unsigned& epoc
     atomicAdd(&a.bar[0], 1u);
     const unsigned target = epoch * gridDim.x;
     unsigned spins = 0;
+#ifdef MYC_BARRIER_BACKOFF
+    while (ld_acquire_gpu(&a.bar[0]) < target) {
+      __nanosleep(MYC_BARRIER_BACKOFF);
+      if (++spins > FU_SPIN_LIMIT) __trap();
+    }
+#else
     while (ld_acquire_gpu(&a.bar[0]) < target)
       if (++spins > FU_SPIN_LIMIT) __trap();
+#endif
     __threadfence();
   }
   __syncthreads();
