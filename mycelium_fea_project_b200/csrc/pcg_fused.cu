@@ -254,24 +254,29 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     }
   };
 
-  // z = M^-1 r for one node (block-Jacobi): 3x3 inverse block times the node's residual
-  auto block3_apply = [&](int64_t nd, const double (&rr)[3], double (&z)[3]) {
-    const double* m = a.binv + 9 * nd;
-    z[0] = m[0] * rr[0] + m[1] * rr[1] + m[2] * rr[2];
-    z[1] = m[3] * rr[0] + m[4] * rr[1] + m[5] * rr[2];
-    z[2] = m[6] * rr[0] + m[7] * rr[1] + m[8] * rr[2];
+  // Block-Jacobi passes use 30 lanes per warp = 10 whole nodes, rows dealt coalesced; the lane of
+  // row (node, c) gets its siblings' residuals by shuffle and applies row c of the 3x3 inverse.
+  const int64_t b3_stride = n_warps * 30;
+  const int b3_sib = lane - lane % 3;                     // first lane of this lane's node
+  auto block3_z = [&](int64_t i, double ri) -> double {   // all 32 lanes call; lanes >= 30 / i >= n idle
+    const double r0 = __shfl_sync(0xffffffffu, ri, b3_sib < 30 ? b3_sib : 0);
+    const double r1 = __shfl_sync(0xffffffffu, ri, b3_sib < 30 ? b3_sib + 1 : 0);
+    const double r2 = __shfl_sync(0xffffffffu, ri, b3_sib < 30 ? b3_sib + 2 : 0);
+    if (lane >= 30 || i >= n) return 0.0;
+    const double* m = a.binv + 3 * i;                     // row c of node i/3: binv[9*(i/3) + 3*c .. +2]
+    return m[0] * r0 + m[1] * r1 + m[2] * r2;
   };
   // init: u = M^-1 r, p = s = 0
   if constexpr (BLOCK3) {
-    for (int64_t nd = gtid; nd < n / 3; nd += gstride) {
-      const double rr[3] = {a.r[3 * nd], a.r[3 * nd + 1], a.r[3 * nd + 2]};
-      double z[3];
-      block3_apply(nd, rr, z);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        put_u(3 * nd + c, z[c]);
-        a.p[3 * nd + c] = 0.0;
-        a.s[3 * nd + c] = 0.0;
+    for (int64_t base = gw * 30; base < n; base += b3_stride) {
+      const int64_t i = base + lane;
+      const bool ok = lane < 30 && i < n;
+      const double ri = ok ? a.r[i] : 0.0;
+      const double z = block3_z(i, ri);
+      if (ok) {
+        put_u(i, z);
+        a.p[i] = 0.0;
+        a.s[i] = 0.0;
       }
     }
   } else {
@@ -386,22 +391,21 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     const double alpha = gamma / denom;
     // ---- phase B: all vector recurrences in one pass
     if constexpr (BLOCK3) {
-      for (int64_t nd = gtid; nd < n / 3; nd += gstride) {
-        double rr[3], z[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int64_t i = 3 * nd + c;
+      for (int64_t base = gw * 30; base < n; base += b3_stride) {
+        const int64_t i = base + lane;
+        const bool ok = lane < 30 && i < n;
+        double ri = 0.0;
+        if (ok) {
           const double pi = u[a.row_offset + i] + beta * a.p[i];
           const double si = a.w[i] + beta * a.s[i];
           a.p[i] = pi;
           a.s[i] = si;
           a.x[i] += alpha * pi;
-          rr[c] = a.dinv[i] != 0.0 ? a.r[i] - alpha * si : 0.0;
-          a.r[i] = rr[c];
+          ri = a.dinv[i] != 0.0 ? a.r[i] - alpha * si : 0.0;
+          a.r[i] = ri;
         }
-        block3_apply(nd, rr, z);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) put_u(3 * nd + c, z[c]);
+        const double z = block3_z(i, ri);
+        if (ok) put_u(i, z);
       }
     } else {
       for (int64_t i = gtid; i < n; i += gstride) {
