@@ -324,7 +324,7 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
         // bytes the sweep streams per iteration: CSR 12 B/nnz, symmetric block view 52 B per 9 nnz
         const double mat = op_used == 2 ? (52.0 / 9.0) * h_nnz : 12.0 * h_nnz;
         ctx->prof_bytes += ((double)fin.iters + 1.0) * (mat + 20.0 * (double)n_rows) +
-                           (double)fin.iters * 96.0 * (double)n_rows;
+                           (double)fin.iters * (block3 ? 120.0 : 96.0) * (double)n_rows;   // + 3x3 inverse blocks
         ctx->prof_op = op_used;
       }
       if (h_out_iters) *h_out_iters = (int64_t)fin.iters;

@@ -214,7 +214,7 @@ class DistributedSolver:
         self._install_plan()
         return dv.true_residual(self.ctx, K, system, x)
 
-    def load_case(self, K, known_dofs, known_vals, react_dofs=None, rtol=1e-10, precond="jacobi",
+    def load_case(self, K, known_dofs, known_vals, react_dofs=None, rtol=1e-10, precond="block3",
                   maxit=500_000, reg=1e-12, gather_U=True):
         """Returns dict(U (global, on every rank if gather_U), iterations, relres, total_force)."""
         import torch

@@ -49,7 +49,7 @@ REGULARISATION = 1e-12          # fea_solver.py:125
 # solver knobs (not in the reference, which uses a direct solve)
 PCG_RTOL = 1e-10
 PCG_MAXIT = 500_000
-PCG_PRECOND = "jacobi"          # or "block3"
+PCG_PRECOND = "block3"          # 3x3 node-block Jacobi (or "jacobi": point Jacobi)
 
 
 def _ctx():
