@@ -381,7 +381,7 @@ def test_host_buffer_entry_point(ctx):
     c = np.ascontiguousarray(coords); a = np.ascontiguousarray(n1, dtype=np.int32); b = np.ascontiguousarray(n2, dtype=np.int32)
     p = lambda arr: arr.ctypes.data_as(C.c_void_p)
     rc = lib.myc_load_case_host(ctx.h, p(c), p(a), p(b), None, len(a), len(c), float(fs.E_mod), fs.A, fs.I,
-                                p(kd), p(kv), len(kd), 1e-12, 0, 1e-12, 100000, p(react), len(react), p(U),
+                                p(kd), p(kv), len(kd), 1e-12, {"jacobi": 0, "block3": 1}[fs.PCG_PRECOND], 1e-12, 100000, p(react), len(react), p(U),
                                 C.byref(force), C.byref(iters), C.byref(rel), C.byref(nnz), C.byref(msa), C.byref(mss))
     check(ctx.h, rc)
     mesh = dv.DeviceMesh.from_host(coords, n1, n2)
