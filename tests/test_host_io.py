@@ -29,3 +29,27 @@ def test_generator_is_seeded_and_matches_survey_counts():
     assert np.all(a1 < b1) and c1[:, 2].max() == 0.0
     c3, _, _ = synth_network(64, seed=1)
     assert len(c3) != len(c1) or not np.array_equal(c3, c1)
+
+
+def test_converter_roundtrips_reference_snapshot(golden_dir, tmp_path):
+    """csv -> mesh.npz -> csv on a committed reference snapshot: the values the reference's reader
+    sees (pandas default parser) survive both directions unchanged."""
+    import gzip
+    import os
+    import pandas as pd
+    from mycelium_fea_project_b200 import snapshot_io
+    src = os.path.join(golden_dir, "ref_results", "sim_20251117_181147")
+    for f in ("nodes.csv", "elements.csv"):
+        with gzip.open(os.path.join(src, f + ".gz")) as fi, open(tmp_path / f, "wb") as fo:
+            fo.write(fi.read())
+    nodes0 = pd.read_csv(tmp_path / "nodes.csv"); elems0 = pd.read_csv(tmp_path / "elements.csv")
+    snapshot_io.csv_to_npz(str(tmp_path))
+    z = np.load(tmp_path / "mesh.npz")
+    assert np.array_equal(z["coords"], nodes0[["x", "y", "z"]].values)
+    assert np.array_equal(z["n1"], elems0["n1"].values) and np.array_equal(z["n2"], elems0["n2"].values)
+    os.remove(tmp_path / "nodes.csv"); os.remove(tmp_path / "elements.csv")
+    snapshot_io.npz_to_csv(str(tmp_path))
+    nodes1 = pd.read_csv(tmp_path / "nodes.csv"); elems1 = pd.read_csv(tmp_path / "elements.csv")
+    assert list(nodes1.columns) == list(nodes0.columns) and list(elems1.columns) == list(elems0.columns)
+    assert np.abs(nodes1[["x", "y", "z"]].values - nodes0[["x", "y", "z"]].values).max() <= 1e-15
+    assert elems1.equals(elems0)
