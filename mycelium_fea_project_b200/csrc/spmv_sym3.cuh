@@ -25,7 +25,10 @@
 struct TmCfgSym {
   static constexpr int NODES = 10;          // nodes per warp tile
   static constexpr int ROWS = 30;           // one lane per row in the sum phase
-  static constexpr int CAPB = 64;           // blocks a stage window may hold (10 nodes x 5 + slack)
+#ifndef TM_SYM_CAPB
+#define TM_SYM_CAPB 64
+#endif
+  static constexpr int CAPB = TM_SYM_CAPB;  // blocks a stage window may hold (10 nodes x 5 + alignment slack)
 };
 __host__ __device__ constexpr size_t tm_sym_smem_per_warp() {
   return (size_t)TM_STAGES * TmCfgSym::CAPB * (6 * sizeof(double) + sizeof(int32_t));
@@ -202,7 +205,7 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
         }
         // one lane per block; CAPB = 64 -> at most two rounds
 #pragma unroll
-        for (int u = 0; u < CAPB / 32; ++u) {
+        for (int u = 0; u < (CAPB + 31) / 32; ++u) {
           const int k = first + lane + 32 * u;
           const int32_t c = k < last ? sc[k] : 0;
           bool remote = false;
