@@ -26,7 +26,7 @@ struct TmCfgSym {
   static constexpr int NODES = 10;          // nodes per warp tile
   static constexpr int ROWS = 30;           // one lane per row in the sum phase
 #ifndef TM_SYM_CAPB
-#define TM_SYM_CAPB 64
+#define TM_SYM_CAPB 56
 #endif
   static constexpr int CAPB = TM_SYM_CAPB;  // blocks a stage window may hold (10 nodes x 5 + alignment slack)
 };
@@ -203,7 +203,7 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
           }
           __syncwarp();
         }
-        // one lane per block; CAPB = 64 -> at most two rounds
+        // one lane per block; CAPB <= 64 -> at most two rounds
 #pragma unroll
         for (int u = 0; u < (CAPB + 31) / 32; ++u) {
           const int k = first + lane + 32 * u;
