@@ -168,7 +168,7 @@ def run_reference(args):
 
 def workload_config(args, n_dof):
     return {"workload": f"synthetic {args.grid}x{args.grid} mycelium occupancy grid per GPU (BASELINE configs[1]), "
-                        f"X and Y load cases, specimen cross-section x{args.gpus}",
+                        f"{' and '.join(n_dof.keys())} load case(s), specimen cross-section x{args.gpus}",
             "grid": args.grid, "n_dof": n_dof, "load_cases": list(n_dof.keys()), "solver": f"{args.precond}-PCG",
             "rtol": RTOL, "grip_length": GRIP, "seed": 0,
             "l2": "operator is L2-resident at grid 512 (no flush inside a solve; see roofline_hbm for the >L2 case)",
@@ -400,7 +400,8 @@ def hbm_roofline(ctx, dv, fs, peak, peak_src, N=2048):
     ms = float(np.mean(ts))
     nbytes = 12 * K.nnz + 20 * K.n_rows
     ach = nbytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "myc_spmv_kernel<EpiPlain> (y = K x)", "workload": f"synthetic {N}x{N} grid",
+    return {"bound": "hbm", "kernel": "myc_spmv_tma_kernel<TmCfgBlock3, EpiPlain> (y = K x on the CSR: per-warp TMA "
+                                      "bulk-copy ring, node-block multiply/sum)", "workload": f"synthetic {N}x{N} grid",
             "n_rows": K.n_rows, "nnz": K.nnz, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": 1.251e9 if N == 2048 else None,
             "traffic_source": "ncu --set full capture of this kernel on this operator: dram read 1.207 GB + write "
