@@ -169,7 +169,8 @@ def run_reference(args):
 def workload_config(args, n_dof):
     return {"workload": f"synthetic {args.grid}x{args.grid} mycelium occupancy grid per GPU (BASELINE configs[1]), "
                         f"{' and '.join(n_dof.keys())} load case(s), specimen cross-section x{args.gpus}",
-            "grid": args.grid, "n_dof": n_dof, "load_cases": list(n_dof.keys()), "solver": f"{args.precond}-PCG",
+            "grid": args.grid, "n_dof": n_dof, "load_cases": list(n_dof.keys()),
+            "solver": f"{args.precond if args.gpus == 1 or args.precond == 'jacobi' else 'block3'}-PCG",
             "rtol": RTOL, "grip_length": GRIP, "seed": 0,
             "l2": "operator is L2-resident at grid 512 (no flush inside a solve; see roofline_hbm for the >L2 case)",
             "parallelism": f"row-partition x{args.gpus}"}
@@ -292,7 +293,7 @@ def run_ours(args):
                 p["kv"].nbytes + p["react"].nbytes
             d2h += host[c]["U"].nbytes + 8
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-        pc = {"jacobi": 0, "block3": 1}[args.precond]
+        pc = {"jacobi": 0, "block3": 1, "block6": 2, "block12": 3}[args.precond]
 
         def e2e_step():
             for c in cases:
@@ -345,7 +346,8 @@ def run_ours(args):
         ach = spmv_bytes / (spmv_ms * 1e-3) / 1e9
         fused = os.environ.get("MYC_NO_FUSED_PCG") != "1" and (world == 1 or os.environ.get("MYC_NO_PEER") != "1")
         kname = ("pcg_fused_kernel (one persistent launch per solve: TMA sweep over the symmetric 3x3 block view of "
-                 "K + fused dots + vector recurrences per iteration; bytes = (its+1)*(52/9 nnz + 20 n) + its*(96|120) n, "
+                 "K + fused dots + vector recurrences per iteration; bytes = (its+1)*(52/9 nnz + 20 n) + its*(96|120|124|148) n "
+                 "for jacobi|block3|block6|block12, "
                  "i.e. what this kernel has to stream -- 12 nnz instead of 52/9 nnz if MYC_NO_SYM3=1)") if fused else \
             "myc_spmv_tma_kernel<EpiCgAp> (Ap = K p + reg p, fused p.Ap; every 32nd launch sampled)"
         roof = {"bound": "hbm", "kernel": kname,
@@ -460,8 +462,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=512)
-    ap.add_argument("--precond", default="block3", choices=["jacobi", "block3"],
-                    help="3x3 node-block Jacobi (default; 19 %% fewer iterations at the same cost per iteration) or point Jacobi")
+    ap.add_argument("--precond", default=os.environ.get("MYC_PCG_PRECOND", "block3"),
+                    choices=["jacobi", "block3", "block6", "block12"],
+                    help="block-Jacobi over 3x3 node blocks (default), over aligned groups of 2 / 4 nodes (block6 / block12, "
+                         "single GPU; N > 1 uses block3), or point Jacobi")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-roofline", action="store_true")
     args = ap.parse_args()

@@ -47,7 +47,12 @@ typedef struct myc_ctx myc_ctx;
 
 /* preconditioners of myc_pcg_solve (the reference's PETSc menu has jacobi / bjacobi:
  * src/fea_petsc_solverAndPC.cpp:331, src/fea_petsc_parallel.cpp:339) */
-enum { MYC_PC_JACOBI = 0, MYC_PC_BLOCK3 = 1 };
+enum {
+  MYC_PC_JACOBI = 0,   /* point Jacobi                                                          */
+  MYC_PC_BLOCK3 = 1,   /* 3x3 node blocks                                                       */
+  MYC_PC_BLOCK6 = 2,   /* aligned blocks of 2 consecutive nodes (rows 6k .. 6k+5)               */
+  MYC_PC_BLOCK12 = 3   /* aligned blocks of 4 consecutive nodes (rows 12k .. 12k+11)            */
+};
 
 int myc_abi_version(void);
 
@@ -135,6 +140,15 @@ int myc_block3_inverse(myc_ctx* ctx, int64_t n_rows, int64_t row_offset, const i
                        const int32_t* d_col_idx, const double* d_val, const double* d_dinv,
                        double reg, double* d_out_binv, void* stream);
 
+/* Node-group block Jacobi (MYC_PC_BLOCK6 / MYC_PC_BLOCK12): inverse of the aligned diagonal blocks of
+ * nodes_per_block (2 or 4) consecutive nodes -- R = 3*nodes_per_block rows -- of K + reg*I, rows/cols
+ * of known DOFs (and the padding of a ragged last block) zeroed.  Stored symmetric-packed: block b
+ * occupies R(R+1)/2 doubles at d_out_pinv + b*R(R+1)/2, entry (i <= j) at i*R - i(i-1)/2 + (j-i).
+ * d_out_pinv: ceil(n_rows/R) * R(R+1)/2 doubles.  Single GPU (row_offset must be a multiple of R). */
+int myc_block_inverse_packed(myc_ctx* ctx, int nodes_per_block, int64_t n_rows, int64_t row_offset,
+                             const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
+                             const double* d_dinv, double reg, double* d_out_pinv, void* stream);
+
 /* Structure parity aid: the explicit reduced matrix K[free][:,free] the reference builds
  * (src/fea_solver.py:118), as CSR over the compacted free numbering.  Two-phase like assembly:
  * call with d_out_col_idx == NULL to get row_ptr + nnz, then again with buffers. */
@@ -156,7 +170,9 @@ int myc_spmv(myc_ctx* ctx, int64_t n_rows, const int32_t* d_row_ptr, const int32
  *     KSPSolve with KSPCG (src/fea_petsc.cpp:323-341, src/fea_petsc_parallel.cpp:330-351).
  * Solves A x = b with A as defined under myc_apply_dirichlet.  d_x (n_rows) holds the initial
  * guess on entry (must be 0 on known rows) and the solution on return.  Converged when
- * ||r||2 <= max(rtol*||b||2, atol).  d_binv may be NULL unless precond == MYC_PC_BLOCK3.
+ * ||r||2 <= max(rtol*||b||2, atol).  d_binv: NULL for MYC_PC_JACOBI, the output of myc_block3_inverse
+ * for MYC_PC_BLOCK3, of myc_block_inverse_packed for MYC_PC_BLOCK6 / MYC_PC_BLOCK12 (those two run only
+ * in the single-GPU persistent solver kernel and return MYC_ERR_STATE where it is unavailable).
  * On a distributed context (myc_dist_init) every rank calls this collectively; dot products
  * are NCCL all-reduces and the search direction's halo is exchanged every iteration.
  * h_out_iters / h_out_relres (||r||/||b|| from the recurrence) may be NULL.

@@ -22,6 +22,9 @@ MYC_ERR_CAPACITY = -6
 MYC_ERR_STATE = -7
 MYC_PC_JACOBI = 0
 MYC_PC_BLOCK3 = 1
+MYC_PC_BLOCK6 = 2
+MYC_PC_BLOCK12 = 3
+PRECONDITIONERS = {"jacobi": MYC_PC_JACOBI, "block3": MYC_PC_BLOCK3, "block6": MYC_PC_BLOCK6, "block12": MYC_PC_BLOCK12}
 
 _ERR_NAMES = {-1: "BAD_ARG", -2: "CUDA", -3: "NCCL", -4: "NOT_CONVERGED", -5: "BREAKDOWN",
               -6: "CAPACITY", -7: "STATE"}
@@ -67,6 +70,7 @@ SIGNATURES = {
     "myc_assemble_numeric": [_p, _p, _p, _p, _f64, _f64, _f64, _i64, _p, _p, _p, _p],
     "myc_apply_dirichlet": [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _f64, _p, _p, _p, _p],
     "myc_block3_inverse": [_p, _i64, _i64, _p, _p, _p, _p, _f64, _p, _p],
+    "myc_block_inverse_packed": [_p, _int, _i64, _i64, _p, _p, _p, _p, _f64, _p, _p],
     "myc_reduce_csr": [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _pi64, _pi64, _p],
     "myc_spmv": [_p, _i64, _p, _p, _p, _p, _p, _p],
     "myc_pcg_solve": [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _int, _f64, _f64, _f64, _i64, _p,

@@ -126,6 +126,13 @@ static inline int myc_ensure(myc_ctx* ctx, DevBuf& b, size_t bytes) {
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Symmetric-packed (upper triangle, row-major) position of entry (i, j) of an R x R block:
+// the layout of myc_block_inverse_packed, read back by the fused PCG kernel.
+__host__ __device__ __forceinline__ constexpr int myc_sympack(int R, int i, int j) {
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  return lo * R - lo * (lo - 1) / 2 + (hi - lo);
+}
+
 // Grid for grid-stride kernels: whole waves of the SM count, never more than the work.
 static inline int grid_for(const myc_ctx* ctx, int64_t n_tiles, int blocks_per_sm) {
   int64_t full = (int64_t)ctx->sm_count * blocks_per_sm;

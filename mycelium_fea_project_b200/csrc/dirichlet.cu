@@ -172,6 +172,86 @@ block3_kernel(int64_t n_nodes_local, int64_t row_offset, const int32_t* __restri
   }
 }
 
+// ---- aligned R x R diagonal-block inverse (R = 6, 12), symmetric-packed --------------------------
+// One thread per block: gather the block from the CSR rows, regularise, replace known / padded
+// rows and columns by identity, invert in place by Gauss-Jordan (the block is a principal submatrix
+// of K_ff + reg I, hence SPD: no pivoting needed), store the symmetrised upper triangle.  A block
+// that is singular in floating point keeps only the inverses of its 3x3 node blocks.
+template <int R>
+__global__ void __launch_bounds__(128)
+block_inverse_kernel(int64_t n_blocks, int64_t n_rows, int64_t row_offset, const int32_t* __restrict__ rp,
+                     const int32_t* __restrict__ ci, const double* __restrict__ v,
+                     const double* __restrict__ dinv, double reg, double* __restrict__ pinv) {
+  for (int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; blk < n_blocks;
+       blk += (int64_t)gridDim.x * blockDim.x) {
+    double m[R][R];
+    bool fr[R];
+    const int64_t r0 = blk * R;
+    const int64_t c0 = row_offset + r0;
+    for (int a = 0; a < R; ++a) {
+      for (int c = 0; c < R; ++c) m[a][c] = 0.0;
+      const int64_t i = r0 + a;
+      fr[a] = i < n_rows && dinv[i] != 0.0;
+      if (fr[a]) {
+        for (int32_t j = rp[i]; j < rp[i + 1]; ++j) {
+          const int64_t c = (int64_t)ci[j] - c0;
+          if (c >= 0 && c < R) m[a][c] += v[j];
+        }
+        m[a][a] += reg;
+      }
+    }
+    double m0[R][R];                                   // the block before elimination (fallback below)
+    for (int a = 0; a < R; ++a)
+      for (int c = 0; c < R; ++c) {
+        if (!fr[a] || !fr[c]) m[a][c] = (a == c) ? 1.0 : 0.0;
+        m0[a][c] = m[a][c];
+      }
+    bool bad = false;
+    for (int k = 0; k < R; ++k) {
+      // a pivot that cancelled below 1e-13 of its diagonal entry carries no digits: meshes with
+      // coincident nodes couple two nodes with ~1e28 and the coupled block is singular in fp64
+      if (!(m[k][k] > 1e-13 * m0[k][k])) { bad = true; break; }
+      const double piv = 1.0 / m[k][k];
+      m[k][k] = 1.0;
+      for (int c = 0; c < R; ++c) m[k][c] *= piv;
+      for (int a = 0; a < R; ++a) {
+        if (a == k) continue;
+        const double f = m[a][k];
+        m[a][k] = 0.0;
+        for (int c = 0; c < R; ++c) m[a][c] -= f * m[k][c];
+      }
+    }
+    if (!bad)
+      for (int a = 0; a < R; ++a)
+        for (int c = 0; c < R; ++c)
+          if (!isfinite(m[a][c])) bad = true;
+    if (bad) {   // this block falls back to its 3x3 node blocks (what MYC_PC_BLOCK3 applies)
+      for (int a = 0; a < R; ++a)
+        for (int c = 0; c < R; ++c) m[a][c] = 0.0;
+      for (int q = 0; q < R; q += 3) {
+        const double a00 = m0[q][q], a01 = m0[q][q + 1], a02 = m0[q][q + 2];
+        const double a10 = m0[q + 1][q], a11 = m0[q + 1][q + 1], a12 = m0[q + 1][q + 2];
+        const double a20 = m0[q + 2][q], a21 = m0[q + 2][q + 1], a22 = m0[q + 2][q + 2];
+        const double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+        const double id = 1.0 / (a00 * c00 + a01 * c01 + a02 * c02);
+        m[q][q] = c00 * id;
+        m[q][q + 1] = (a02 * a21 - a01 * a22) * id;
+        m[q][q + 2] = (a01 * a12 - a02 * a11) * id;
+        m[q + 1][q] = c01 * id;
+        m[q + 1][q + 1] = (a00 * a22 - a02 * a20) * id;
+        m[q + 1][q + 2] = (a02 * a10 - a00 * a12) * id;
+        m[q + 2][q] = c02 * id;
+        m[q + 2][q + 1] = (a01 * a20 - a00 * a21) * id;
+        m[q + 2][q + 2] = (a00 * a11 - a01 * a10) * id;
+      }
+    }
+    double* out = pinv + blk * (R * (R + 1) / 2);
+    for (int a = 0; a < R; ++a)
+      for (int c = a; c < R; ++c)
+        out[myc_sympack(R, a, c)] = (fr[a] && fr[c]) ? 0.5 * (m[a][c] + m[c][a]) : 0.0;
+  }
+}
+
 }  // namespace
 
 extern "C" int myc_apply_dirichlet(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
@@ -243,6 +323,28 @@ extern "C" int myc_block3_inverse(myc_ctx* ctx, int64_t n_rows, int64_t row_offs
   MYC_CUDA(ctx, cudaSetDevice(ctx->device));
   block3_kernel<<<grid_for(ctx, ceil_div64(n_rows / 3, DI_THREADS), 8), DI_THREADS, 0, (cudaStream_t)stream>>>(
       n_rows / 3, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv, reg, d_out_binv);
+  MYC_LAUNCHED(ctx);
+  return MYC_OK;
+}
+
+extern "C" int myc_block_inverse_packed(myc_ctx* ctx, int nodes_per_block, int64_t n_rows, int64_t row_offset,
+                                        const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
+                                        const double* d_dinv, double reg, double* d_out_pinv, void* stream) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  const int R = 3 * nodes_per_block;
+  if ((nodes_per_block != 2 && nodes_per_block != 4) || n_rows < 0 || row_offset < 0 || row_offset % R ||
+      !d_row_ptr || (n_rows > 0 && (!d_col_idx || !d_val || !d_dinv || !d_out_pinv)))
+    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "block_inverse_packed: bad argument (nodes_per_block 2 or 4, row_offset a multiple of the block size)");
+  if (n_rows == 0) return MYC_OK;
+  MYC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n_blocks = ceil_div64(n_rows, R);
+  const int grid = grid_for(ctx, ceil_div64(n_blocks, 128), 8);
+  if (nodes_per_block == 2)
+    block_inverse_kernel<6><<<grid, 128, 0, (cudaStream_t)stream>>>(n_blocks, n_rows, row_offset, d_row_ptr, d_col_idx,
+                                                                    d_val, d_dinv, reg, d_out_pinv);
+  else
+    block_inverse_kernel<12><<<grid, 128, 0, (cudaStream_t)stream>>>(n_blocks, n_rows, row_offset, d_row_ptr, d_col_idx,
+                                                                     d_val, d_dinv, reg, d_out_pinv);
   MYC_LAUNCHED(ctx);
   return MYC_OK;
 }

@@ -23,7 +23,7 @@ int myc_dist_allreduce_dev(myc_ctx* ctx, double* d_buf, int n, cudaStream_t st);
 int myc_dist_halo(myc_ctx* ctx, double* d_x_global, cudaStream_t st);              // dist.cu
 int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
                       const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
-                      const double* d_dinv, const double* d_binv, double reg, int64_t maxit, double* d_x,
+                      const double* d_dinv, const double* d_binv, int pc, double reg, int64_t maxit, double* d_x,
                       cudaStream_t st, int* handled, int* op_used);                 // pcg_fused.cu
 
 namespace {
@@ -265,10 +265,13 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
                              int precond, double reg, double rtol, double atol, int64_t maxit,
                              double* d_x, int64_t* h_out_iters, double* h_out_relres, void* stream) {
   if (!ctx) return MYC_ERR_BAD_ARG;
+  if (n_rows == 0 && (precond == MYC_PC_BLOCK6 || precond == MYC_PC_BLOCK12)) precond = MYC_PC_JACOBI;   // nothing to solve
   const bool block3 = precond == MYC_PC_BLOCK3;
+  const bool group = precond == MYC_PC_BLOCK6 || precond == MYC_PC_BLOCK12;     // fused single-GPU kernel only
   if (n_rows < 0 || n_cols_global < n_rows || row_offset < 0 || row_offset + n_rows > n_cols_global ||
       !d_row_ptr || (n_rows > 0 && (!d_rhs || !d_dinv || !d_x)) || maxit < 0 ||
-      (precond != MYC_PC_JACOBI && precond != MYC_PC_BLOCK3) || (block3 && (!d_binv || n_rows % 3)))
+      (precond != MYC_PC_JACOBI && !block3 && !group) || (block3 && (!d_binv || n_rows % 3)) ||
+      (group && n_rows > 0 && !d_binv))
     MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "pcg_solve: bad argument");
   MYC_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -299,7 +302,7 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
     int handled = 0, op_used = 0;
     if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
     MYC_TRY(myc_pcg_fused_try(ctx, n_rows, n_cols_global, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv,
-                              block3 ? d_binv : nullptr, reg, maxit, d_x, st, &handled, &op_used));
+                              (block3 || group) ? d_binv : nullptr, precond, reg, maxit, d_x, st, &handled, &op_used));
     if (handled) {
       if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
       MYC_CUDA(ctx, cudaMemcpyAsync(h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
@@ -324,7 +327,8 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
         // bytes the sweep streams per iteration: CSR 12 B/nnz, symmetric block view 52 B per 9 nnz
         const double mat = op_used == 2 ? (52.0 / 9.0) * h_nnz : 12.0 * h_nnz;
         ctx->prof_bytes += ((double)fin.iters + 1.0) * (mat + 20.0 * (double)n_rows) +
-                           (double)fin.iters * (block3 ? 120.0 : 96.0) * (double)n_rows;   // + 3x3 inverse blocks
+                           (double)fin.iters * (double)n_rows *           // + the inverse blocks of the preconditioner
+                               (precond == MYC_PC_BLOCK12 ? 148.0 : precond == MYC_PC_BLOCK6 ? 124.0 : block3 ? 120.0 : 96.0);
         ctx->prof_op = op_used;
       }
       if (h_out_iters) *h_out_iters = (int64_t)fin.iters;
@@ -338,6 +342,10 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       return MYC_OK;
     }
   }
+  if (group)
+    MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve: MYC_PC_BLOCK6 / MYC_PC_BLOCK12 run only in the single-GPU persistent solver "
+                                 "kernel, which is unavailable here (multi-GPU context, MYC_NO_FUSED_PCG, unaligned arrays "
+                                 "or no cooperative launch): use MYC_PC_BLOCK3");
   if (block3)
     pcg_init_kernel<true><<<vgrid, VEC_THREADS, 0, st>>>(n_rows, row_offset, r, d_dinv, d_binv, pg, zv, partials, sc);
   else

@@ -56,7 +56,8 @@ struct FusedArgs {
   const int32_t* bcol;
   int32_t nb_total;
   const double* dinv;
-  const double* binv;      // (n_rows/3, 9) block-Jacobi inverse, or null for point Jacobi
+  const double* binv;      // block-Jacobi inverses: (n_rows/3, 9) for PC 1, symmetric-packed R x R blocks for PC 2 / 3
+                           // (myc_block_inverse_packed), null for point Jacobi
   double* x;
   double* r;
   double* w;
@@ -141,14 +142,23 @@ __device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoc
 }
 
 // Single-GPU barrier: every block spins on the arrive counter itself (no leader hop).
+// -DMYC_LIGHT_BARRIER (A/B build): the arrive is one release-atomic and the wait one acquire-load spin,
+// instead of __threadfence() + atomicAdd ... spin + __threadfence() (each fence compiles to
+// MEMBAR.ALL.CTA + MEMBAR.SC.GPU + ERRBAR + CCTL.IVALL).  Release covers the block's stores through the
+// preceding bar.sync (cumulativity); the acquire-load's CCTL.IVALL invalidates the SM's L1 for every warp.
 __device__ __forceinline__ void local_barrier(const FusedArgs& a, unsigned& epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
     ++epoch;
-    __threadfence();
-    atomicAdd(&a.bar[0], 1u);
     const unsigned target = epoch * gridDim.x;
     unsigned spins = 0;
+#ifdef MYC_LIGHT_BARRIER
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(&a.bar[0]), "r"(1u) : "memory");
+    while (ld_acquire_gpu(&a.bar[0]) < target)
+      if (++spins > FU_SPIN_LIMIT) __trap();
+#else
+    __threadfence();
+    atomicAdd(&a.bar[0], 1u);
 #ifdef MYC_BARRIER_BACKOFF
     while (ld_acquire_gpu(&a.bar[0]) < target) {
       __nanosleep(MYC_BARRIER_BACKOFF);
@@ -159,6 +169,7 @@ __device__ __forceinline__ void local_barrier(const FusedArgs& a, unsigned& epoc
       if (++spins > FU_SPIN_LIMIT) __trap();
 #endif
     __threadfence();
+#endif
   }
   __syncthreads();
 }
@@ -192,9 +203,14 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define FT_MARK(k) do { } while (0)
 #endif
 
+// PC: 0 = point Jacobi, 1 = 3x3 node blocks, 2 / 3 = aligned blocks of 2 / 4 nodes (6 / 12 rows, single GPU)
 // OP: 0 = generic CSR sweep, 1 = node-block CSR sweep, 2 = symmetric 3x3 block operator
-template <bool BLOCK3, int OP, bool DIST>
+template <int PC, int OP, bool DIST>
 __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
+  constexpr bool BLOCK3 = PC == 1;
+  constexpr int GR = PC == 2 ? 6 : 12;                 // rows per block of the node-group preconditioners
+  constexpr int GLW = (32 / GR) * GR;                  // lanes of a warp that carry rows: 30 (GR 6), 24 (GR 12)
+  static_assert(PC >= 0 && PC <= 3 && !(DIST && PC >= 2), "node-group blocks are single-GPU");
   using Cfg = std::conditional_t<OP == 1, TmCfgBlock3, TmCfgGeneric>;
   using Pipe = std::conditional_t<OP == 2, TmSymPipe, TmPipe>;
   extern __shared__ __align__(128) unsigned char fu_smem[];
@@ -266,8 +282,35 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     const double* m = a.binv + 3 * i;                     // row c of node i/3: binv[9*(i/3) + 3*c .. +2]
     return m[0] * r0 + m[1] * r1 + m[2] * r2;
   };
+  // Node-group passes: GLW lanes per warp = whole blocks of GR rows; the lane of row c of a block gets
+  // its siblings' residuals by shuffle and applies row c of the symmetric-packed inverse.
+  const int64_t g_stride = n_warps * GLW;
+  const int g_c = lane % GR, g_first = lane - lane % GR;
+  auto group_z = [&](int64_t i, double ri) -> double {    // all 32 lanes call; lanes >= GLW / i >= n idle
+    const bool ok = lane < GLW && i < n;
+    const double* m = a.binv + (ok ? i / GR : 0) * (GR * (GR + 1) / 2);
+    double z = 0.0;
+#pragma unroll
+    for (int j = 0; j < GR; ++j) {
+      const double rj = __shfl_sync(0xffffffffu, ri, lane < GLW ? g_first + j : 0);
+      if (ok) z += m[myc_sympack(GR, g_c, j)] * rj;
+    }
+    return z;
+  };
   // init: u = M^-1 r, p = s = 0
-  if constexpr (BLOCK3) {
+  if constexpr (PC >= 2) {
+    for (int64_t base = gw * GLW; base < n; base += g_stride) {
+      const int64_t i = base + lane;
+      const bool ok = lane < GLW && i < n;
+      const double ri = ok ? a.r[i] : 0.0;
+      const double z = group_z(i, ri);
+      if (ok) {
+        put_u(i, z);
+        a.p[i] = 0.0;
+        a.s[i] = 0.0;
+      }
+    }
+  } else if constexpr (BLOCK3) {
     for (int64_t base = gw * 30; base < n; base += b3_stride) {
       const int64_t i = base + lane;
       const bool ok = lane < 30 && i < n;
@@ -390,7 +433,24 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     if (!(denom > 0.0) || !isfinite(gamma)) { status = 2; break; }
     const double alpha = gamma / denom;
     // ---- phase B: all vector recurrences in one pass
-    if constexpr (BLOCK3) {
+    if constexpr (PC >= 2) {
+      for (int64_t base = gw * GLW; base < n; base += g_stride) {
+        const int64_t i = base + lane;
+        const bool ok = lane < GLW && i < n;
+        double ri = 0.0;
+        if (ok) {
+          const double pi = u[a.row_offset + i] + beta * a.p[i];
+          const double si = a.w[i] + beta * a.s[i];
+          a.p[i] = pi;
+          a.s[i] = si;
+          a.x[i] += alpha * pi;
+          ri = a.dinv[i] != 0.0 ? a.r[i] - alpha * si : 0.0;
+          a.r[i] = ri;
+        }
+        const double z = group_z(i, ri);
+        if (ok) put_u(i, z);
+      }
+    } else if constexpr (BLOCK3) {
       for (int64_t base = gw * 30; base < n; base += b3_stride) {
         const int64_t i = base + lane;
         const bool ok = lane < 30 && i < n;
@@ -506,16 +566,20 @@ extern "C" int myc_dist_peer_open(myc_ctx* ctx, const uint8_t* h_handles) {
 // sc->tol2 is set (pcg.cu does that for both paths).  *op_used: 0 generic CSR, 1 node-block CSR,
 // 2 symmetric 3x3 block view.
 namespace {
-template <bool B3PC, int OP, bool DIST>
-const void* fused_fn() { return (const void*)pcg_fused_kernel<B3PC, OP, DIST>; }
-// index = dist*6 + op*2 + block3pc
+template <int PC, int OP, bool DIST>
+const void* fused_fn() { return (const void*)pcg_fused_kernel<PC, OP, DIST>; }
+constexpr int FU_VARIANTS = 18;
+// index = dist*6 + op*2 + pc for pc 0 / 1;  12 + op*2 + (pc - 2) for the single-GPU node-group blocks
 const void* fused_variant(int idx) {
-  static const void* tab[12] = {
-      fused_fn<false, 0, false>(), fused_fn<true, 0, false>(), fused_fn<false, 1, false>(), fused_fn<true, 1, false>(),
-      fused_fn<false, 2, false>(), fused_fn<true, 2, false>(), fused_fn<false, 0, true>(),  fused_fn<true, 0, true>(),
-      fused_fn<false, 1, true>(),  fused_fn<true, 1, true>(),  fused_fn<false, 2, true>(),  fused_fn<true, 2, true>()};
+  static const void* tab[FU_VARIANTS] = {
+      fused_fn<0, 0, false>(), fused_fn<1, 0, false>(), fused_fn<0, 1, false>(), fused_fn<1, 1, false>(),
+      fused_fn<0, 2, false>(), fused_fn<1, 2, false>(), fused_fn<0, 0, true>(),  fused_fn<1, 0, true>(),
+      fused_fn<0, 1, true>(),  fused_fn<1, 1, true>(),  fused_fn<0, 2, true>(),  fused_fn<1, 2, true>(),
+      fused_fn<2, 0, false>(), fused_fn<3, 0, false>(), fused_fn<2, 1, false>(), fused_fn<3, 1, false>(),
+      fused_fn<2, 2, false>(), fused_fn<3, 2, false>()};
   return tab[idx];
 }
+int fused_variant_op(int idx) { return (idx % 6) / 2; }
 size_t fused_smem(int op) {
   return op == 2 ? tm_sym_smem_bytes(FU_WARPS) : tm_smem_bytes(FU_WARPS, op == 1 ? TmCfgBlock3::CAP : TmCfgGeneric::CAP);
 }
@@ -523,19 +587,20 @@ size_t fused_smem(int op) {
 
 int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
                       const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
-                      const double* d_dinv, const double* d_binv, double reg, int64_t maxit, double* d_x,
+                      const double* d_dinv, const double* d_binv, int pc, double reg, int64_t maxit, double* d_x,
                       cudaStream_t st, int* handled, int* op_used) {
   *handled = 0;
   if (ctx->no_fused_pcg) return MYC_OK;
   const bool dist = ctx->world > 1;
+  if (pc >= 2 && (dist || row_offset != 0)) return MYC_OK;      // node-group blocks: single GPU only
   if (dist && (!ctx->peer_ok || ctx->peer_cap < n_cols_global || ctx->world > MYC_MAX_WORLD)) return MYC_OK;
   if (!dist && n_rows == 0) return MYC_OK;
   if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;   // (same allocator on every rank)
   static int max_blocks_per_sm = -1;
   if (max_blocks_per_sm < 0) {
     int mn = 1 << 30;
-    for (int k = 0; k < 12; ++k) {
-      const size_t smem = fused_smem((k % 6) / 2);
+    for (int k = 0; k < FU_VARIANTS; ++k) {
+      const size_t smem = fused_smem(fused_variant_op(k));
       int b = 0;
       MYC_CUDA(ctx, cudaFuncSetAttribute(fused_variant(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fused_variant(k), FU_THREADS, smem));
@@ -625,7 +690,7 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
     a.peer_sync[0] = nullptr;
   }
   void* params[] = {&a};
-  const void* fn = fused_variant((dist ? 6 : 0) + op * 2 + (d_binv ? 1 : 0));
+  const void* fn = pc >= 2 ? fused_variant(12 + op * 2 + (pc - 2)) : fused_variant((dist ? 6 : 0) + op * 2 + (pc == 1 ? 1 : 0));
   MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FU_THREADS), params, fused_smem(op), st));
   ctx->launches++;
   *handled = 1;

@@ -145,8 +145,10 @@ class DirichletSystem:
     ubc: torch.Tensor         # (n_cols,)  prescribed values scattered, 0 elsewhere
     rhs: torch.Tensor         # (n_rows,)  -K_fk u_k on free rows
     dinv: torch.Tensor        # (n_rows,)  1/(K_ii+reg) on free rows, 0 on known rows
-    binv: torch.Tensor | None = None   # (n_rows/3, 9) block-Jacobi inverse
+    binv: torch.Tensor | None = None   # block-Jacobi inverses: (n_rows/3, 9) for "block3", symmetric-packed
+                                       # (n_blocks, R(R+1)/2) for "block6" / "block12" (R = 6 / 12 rows per block)
     reg: float = REGULARISATION
+    binv_kind: str | None = None       # which preconditioner ``binv`` belongs to
 
 
 # ---------------------------------------------------------------------------------------------
@@ -174,7 +176,13 @@ def assemble(ctx: Context, mesh: DeviceMesh, E, A, I, node_range=None) -> Device
 
 
 def apply_dirichlet(ctx: Context, K: DeviceCSR, known_dofs: torch.Tensor, known_vals: torch.Tensor,
-                    reg=REGULARISATION, block3=False) -> DirichletSystem:
+                    reg=REGULARISATION, block3=False, precond=None) -> DirichletSystem:
+    """``precond`` ("jacobi", "block3", "block6", "block12") selects which block inverses are built next
+    to the Jacobi diagonal; ``block3=True`` is the older spelling of precond="block3"."""
+    if precond is None:
+        precond = "block3" if block3 else "jacobi"
+    if precond not in _lib.PRECONDITIONERS:
+        raise ValueError(f"unknown preconditioner {precond!r}")
     _hint(ctx, K)
     ubc = torch.empty((K.n_cols,), dtype=torch.float64, device=ctx.device)
     rhs = torch.empty((K.n_rows,), dtype=torch.float64, device=ctx.device)
@@ -183,11 +191,17 @@ def apply_dirichlet(ctx: Context, K: DeviceCSR, known_dofs: torch.Tensor, known_
                                          _ptr(K.val), _ptr(known_dofs), _ptr(known_vals), known_dofs.shape[0],
                                          float(reg), _ptr(ubc), _ptr(rhs), _ptr(dinv), _stream()))
     binv = None
-    if block3:
+    if precond == "block3":
         binv = torch.empty((K.n_rows // 3, 9), dtype=torch.float64, device=ctx.device)
         check(ctx.h, lib.myc_block3_inverse(ctx.h, K.n_rows, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx),
                                             _ptr(K.val), _ptr(dinv), float(reg), _ptr(binv), _stream()))
-    return DirichletSystem(ubc, rhs, dinv, binv, float(reg))
+    elif precond in ("block6", "block12"):
+        npb = 2 if precond == "block6" else 4
+        R = 3 * npb
+        binv = torch.empty(((K.n_rows + R - 1) // R, R * (R + 1) // 2), dtype=torch.float64, device=ctx.device)
+        check(ctx.h, lib.myc_block_inverse_packed(ctx.h, npb, K.n_rows, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx),
+                                                  _ptr(K.val), _ptr(dinv), float(reg), _ptr(binv), _stream()))
+    return DirichletSystem(ubc, rhs, dinv, binv, float(reg), precond if binv is not None else None)
 
 
 def spmv(ctx: Context, K: DeviceCSR, x: torch.Tensor, out: torch.Tensor | None = None):
@@ -202,9 +216,9 @@ def pcg(ctx: Context, K: DeviceCSR, sys: DirichletSystem, x0: torch.Tensor | Non
         rtol=1e-10, atol=0.0, maxit=1_000_000, raise_on_maxit=True):
     """Returns (x, iterations, relres).  x is the solution on free rows (0 on known rows)."""
     x = torch.zeros((K.n_rows,), dtype=torch.float64, device=ctx.device) if x0 is None else x0
-    pc = {"jacobi": _lib.MYC_PC_JACOBI, "block3": _lib.MYC_PC_BLOCK3}[precond]
-    if pc == _lib.MYC_PC_BLOCK3 and sys.binv is None:
-        raise ValueError("block3 preconditioner needs apply_dirichlet(..., block3=True)")
+    pc = _lib.PRECONDITIONERS[precond]
+    if pc != _lib.MYC_PC_JACOBI and (sys.binv is None or sys.binv_kind != precond):
+        raise ValueError(f"{precond} preconditioner needs apply_dirichlet(..., precond={precond!r})")
     iters, relres = C.c_int64(0), C.c_double(0.0)
     _hint(ctx, K)
     rc = lib.myc_pcg_solve(ctx.h, K.n_rows, K.n_cols, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx), _ptr(K.val),

@@ -225,7 +225,11 @@ class DistributedSolver:
         self._install_plan()
         td = lambda a, dt: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
         kd, kv = td(known_dofs, np.int64), td(known_vals, np.float64)
-        sysd = dv.apply_dirichlet(ctx, K, kd, kv, reg, block3=(precond == "block3"))
+        if precond in ("block6", "block12"):
+            # the node-group blocks live in the single-GPU solver kernel only (rank boundaries are not
+            # aligned to node groups): a row-partitioned solve uses the 3x3 node blocks
+            precond = "block3"
+        sysd = dv.apply_dirichlet(ctx, K, kd, kv, reg, precond=precond)
         self._ensure_peer(K.n_cols)
         x, iters, relres = dv.pcg(ctx, K, sysd, precond=precond, rtol=rtol, maxit=maxit)
         U = dv.merge_solution(ctx, K, sysd, x)         # own rows of a zeroed global vector

@@ -49,7 +49,9 @@ REGULARISATION = 1e-12          # fea_solver.py:125
 # solver knobs (not in the reference, which uses a direct solve)
 PCG_RTOL = 1e-10
 PCG_MAXIT = 500_000
-PCG_PRECOND = "block3"          # 3x3 node-block Jacobi (or "jacobi": point Jacobi)
+# "jacobi" (point), "block3" (3x3 node blocks), "block6" / "block12" (aligned blocks of 2 / 4 consecutive
+# nodes; single GPU).  MYC_PCG_PRECOND overrides the default.
+PCG_PRECOND = os.environ.get("MYC_PCG_PRECOND", "block3")
 
 
 def _ctx():
@@ -108,7 +110,7 @@ def solve_system(K, known_dofs, known_vals, return_info=False):
     if len(np.unique(kd)) != len(kd):
         raise ValueError("known_dofs contains duplicates")
     sysd = dv.apply_dirichlet(ctx, Kd, _dev(kd, np.int64), _dev(known_vals, np.float64), REGULARISATION,
-                              block3=(PCG_PRECOND == "block3"))
+                              precond=PCG_PRECOND)
     x, iters, relres = dv.pcg(ctx, Kd, sysd, precond=PCG_PRECOND, rtol=PCG_RTOL, maxit=PCG_MAXIT)
     U = dv.merge_solution(ctx, Kd, sysd, x).cpu().numpy()
     if return_info:
@@ -170,7 +172,7 @@ def analyze_load_case(mesh: dv.DeviceMesh, known_dofs, known_vals, react_dofs=No
         K = dv.assemble(ctx, mesh, E_mod, globals()["A"], globals()["I"])
     ev[1].record()
     sysd = dv.apply_dirichlet(ctx, K, as_dev(known_dofs, np.int64), as_dev(known_vals, np.float64),
-                              REGULARISATION, block3=(precond == "block3"))
+                              REGULARISATION, precond=precond)
     x, iters, relres = dv.pcg(ctx, K, sysd, x0=x0, precond=precond, rtol=rtol, maxit=PCG_MAXIT)
     out = LoadCaseResult()
     out.U = dv.merge_solution(ctx, K, sysd, x)

@@ -330,3 +330,59 @@ def solve_system_pcg(K, known_dofs, known_vals, rtol=1e-10, maxit=200000):
     U[free] = U_f
     U[known_dofs] = known_vals
     return U, it, rel
+
+# ---------------------------------------------------------------------------
+# Checker for the node-group block-Jacobi preconditioners of the CUDA path (MYC_PC_BLOCK3 / 6 / 12):
+# PETSc's PCBJACOBI idea (src/fea_petsc_parallel.cpp:339) with fixed aligned blocks of
+# ``rows_per_block`` consecutive DOFs of the FULL index space, restricted to the free DOFs, inverted
+# exactly.  Not in the reference's scipy path; used only to predict iteration counts and block inverses.
+# ---------------------------------------------------------------------------
+def aligned_block_inverses(K_ff, free, rows_per_block):
+    """Dense inverses of the diagonal blocks of K_ff grouped by ``free // rows_per_block``.
+    Returns (labels (n_free,), {label: (reduced row indices, inverse)})."""
+    labels = np.asarray(free) // rows_per_block
+    A = K_ff.tocsr()
+    out = {}
+    starts = np.flatnonzero(np.r_[True, labels[1:] != labels[:-1]])
+    ends = np.r_[starts[1:], len(labels)]
+    for s, e in zip(starts, ends):
+        idx = np.arange(s, e)
+        out[int(labels[s])] = (idx, np.linalg.inv(A[s:e, s:e].toarray()))
+    return labels, out
+
+
+def block_jacobi_pcg(K_ff, F_f, free, rows_per_block, rtol=1e-10, maxit=200000):
+    """Hestenes-Stiefel PCG on the reduced system with the aligned-block Jacobi preconditioner.
+    Returns (x, iterations, ||r||/||b||)."""
+    A = K_ff.tocsr()
+    _, blocks = aligned_block_inverses(A, free, rows_per_block)
+    # assemble the block-diagonal inverse once as a sparse matrix
+    rows, cols, vals = [], [], []
+    for idx, inv in blocks.values():
+        r, c = np.meshgrid(idx, idx, indexing="ij")
+        rows.append(r.ravel()); cols.append(c.ravel()); vals.append(inv.ravel())
+    Minv = csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=A.shape)
+    b = np.asarray(F_f, dtype=float)
+    x = np.zeros(len(b))
+    bnorm = np.linalg.norm(b)
+    if bnorm == 0.0:
+        return x, 0, 0.0
+    r = b.copy()
+    z = Minv @ r
+    p = z.copy()
+    rz = r @ z
+    it, rn = 0, bnorm
+    while it < maxit:
+        Ap = A @ p
+        alpha = rz / (p @ Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        it += 1
+        rn = np.linalg.norm(r)
+        if rn <= rtol * bnorm:
+            break
+        z = Minv @ r
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, it, rn / bnorm

@@ -36,6 +36,11 @@ def _dev(a, dt):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).cuda()
 
 
+def _lib_preconditioners():
+    from mycelium_fea_project_b200._lib import PRECONDITIONERS
+    return PRECONDITIONERS
+
+
 def _assert_csr_parity(K, Ko):
     assert K.indptr.dtype == np.int32 and K.indices.dtype == np.int32
     assert np.array_equal(K.indptr, Ko.indptr), "row_ptr differs"
@@ -290,7 +295,8 @@ def test_spmv_dense_rows_fallback(ctx):
     assert np.allclose(y, M @ x, rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("N,precond", [(64, "jacobi"), (64, "block3"), (128, "jacobi"), (128, "block3")])
+@pytest.mark.parametrize("N,precond", [(64, "jacobi"), (64, "block3"), (128, "jacobi"), (128, "block3"),
+                                       (64, "block6"), (64, "block12"), (128, "block6"), (128, "block12")])
 def test_solve_golden(N, precond, golden_dir, monkeypatch):
     g = np.load(os.path.join(golden_dir, f"solve_synth{N}.npz"))
     coords, n1, n2 = synth_network(N)
@@ -306,6 +312,85 @@ def test_solve_golden(N, precond, golden_dir, monkeypatch):
     F = K @ U
     tf = F[[3 * n + 1 for n in g["top"]]].sum()
     assert abs(tf - float(g["total_force"])) <= 1e-7 * abs(float(g["total_force"]))
+
+
+@pytest.mark.parametrize("precond,R", [("block6", 6), ("block12", 12)])
+def test_block_inverse_packed_matches_numpy(ctx, precond, R):
+    """myc_block_inverse_packed: aligned R x R diagonal blocks of K + reg I with known rows/cols (and the
+    padding of a ragged last block) removed, inverted, stored as the row-major upper triangle."""
+    coords, n1, n2 = synth_network(40, seed=1)          # 1067 nodes: ragged last block for R = 6 and 12
+    mesh = dv.DeviceMesh.from_host(coords, n1, n2)
+    K = dv.assemble(ctx, mesh, fs.E_mod, fs.A, fs.I)
+    kd, kv = fs.build_bc(*fs.grip_nodes(coords, 0.2), 0.02, -0.02)
+    sysd = dv.apply_dirichlet(ctx, K, _dev(kd, np.int64), _dev(kv, np.float64), precond=precond)
+    n = K.n_rows
+    n_blocks = (n + R - 1) // R
+    P = sysd.binv.cpu().numpy()
+    assert P.shape == (n_blocks, R * (R + 1) // 2)
+    Ks = K.to_scipy().tocsr()
+    known = np.zeros(n, bool)
+    known[kd] = True
+    iu = np.triu_indices(R)
+    worst = 0.0
+    for blk in range(n_blocks):
+        rows = np.arange(blk * R, min(blk * R + R, n))
+        m = len(rows)
+        fr = np.zeros(R, bool)
+        fr[:m] = ~known[rows]
+        full = np.eye(R)
+        full[:m, :m] = Ks[rows][:, rows].toarray() + fs.REGULARISATION * np.eye(m)
+        full[~fr, :] = 0.0
+        full[:, ~fr] = 0.0
+        full[~fr, ~fr] = 1.0
+        inv = np.linalg.inv(full)
+        inv[~fr, :] = 0.0
+        inv[:, ~fr] = 0.0
+        got = np.zeros((R, R))
+        got[iu] = P[blk]
+        got = got + got.T - np.diag(np.diag(got))
+        worst = max(worst, np.abs(got - inv).max() / max(np.abs(inv).max(), 1e-300))
+    print(f"{precond}: {n_blocks} blocks (last one has {n - (n_blocks - 1) * R} rows), worst rel error {worst:.2e}")
+    assert worst <= 1e-6                     # blocks of floating pairs have condition numbers ~1e8
+
+
+@pytest.mark.parametrize("precond,R", [("block3", 3), ("block6", 6), ("block12", 12)])
+def test_block_jacobi_iterations_match_oracle(ctx, precond, R):
+    """The preconditioner the kernel applies is the exact inverse of the aligned diagonal blocks: the
+    iteration count must equal (up to rounding-level drift) that of a numpy PCG with those inverses."""
+    coords, n1, n2 = synth_network(96)
+    mesh = dv.DeviceMesh.from_host(coords, n1, n2)
+    K = dv.assemble(ctx, mesh, fs.E_mod, fs.A, fs.I)
+    kd, kv = fs.build_bc(*fs.grip_nodes(coords, 0.5), 0.02, -0.02)
+    sysd = dv.apply_dirichlet(ctx, K, _dev(kd, np.int64), _dev(kv, np.float64), precond=precond)
+    x, it, rel = dv.pcg(ctx, K, sysd, precond=precond, rtol=1e-10)
+    tr = dv.true_residual(ctx, K, sysd, x)
+    Ko = fo.assemble_global_stiffness(coords, n1, n2, np.ones(len(n1), bool))
+    free, K_ff, F_f = fo.reduce_system(Ko, kd, kv)
+    xo, ito, relo = fo.block_jacobi_pcg(K_ff, F_f, free, R, rtol=1e-10)
+    print(f"{precond}: GPU {it} iterations (relres {rel:.2e}, true {tr:.2e}), numpy {ito} (relres {relo:.2e})")
+    assert abs(it - ito) <= 0.03 * ito + 3
+    assert rel <= 1e-10 and tr <= 1.2e-10
+    assert float(x[_dev(kd, np.int64)].abs().max()) == 0.0     # x stays 0 on known rows
+
+
+def test_group_blocks_need_the_fused_single_gpu_solver(ctx, monkeypatch):
+    from mycelium_fea_project_b200._lib import MyceliumFeaError, MYC_ERR_STATE
+    coords, n1, n2 = synth_network(32)
+    mesh = dv.DeviceMesh.from_host(coords, n1, n2)
+    K = dv.assemble(ctx, mesh, fs.E_mod, fs.A, fs.I)
+    kd, kv = fs.build_bc(*fs.grip_nodes(coords, 0.3), 0.02, -0.02)
+    monkeypatch.setenv("MYC_NO_FUSED_PCG", "1")
+    ctx2 = dv.Context(0)
+    try:
+        sysd = dv.apply_dirichlet(ctx2, K, _dev(kd, np.int64), _dev(kv, np.float64), precond="block6")
+        with pytest.raises(MyceliumFeaError) as ei:
+            dv.pcg(ctx2, K, sysd, precond="block6")
+        assert ei.value.code == MYC_ERR_STATE
+    finally:
+        ctx2.close()
+    sysd = dv.apply_dirichlet(ctx, K, _dev(kd, np.int64), _dev(kv, np.float64), precond="block3")
+    with pytest.raises(ValueError):
+        dv.pcg(ctx, K, sysd, precond="block6")          # inverse blocks of another preconditioner
 
 
 def test_solve_real_snapshot_golden(golden_dir, monkeypatch):
@@ -414,7 +499,7 @@ def test_host_buffer_entry_point(ctx):
     c = np.ascontiguousarray(coords); a = np.ascontiguousarray(n1, dtype=np.int32); b = np.ascontiguousarray(n2, dtype=np.int32)
     p = lambda arr: arr.ctypes.data_as(C.c_void_p)
     rc = lib.myc_load_case_host(ctx.h, p(c), p(a), p(b), None, len(a), len(c), float(fs.E_mod), fs.A, fs.I,
-                                p(kd), p(kv), len(kd), 1e-12, {"jacobi": 0, "block3": 1}[fs.PCG_PRECOND], 1e-12, 100000, p(react), len(react), p(U),
+                                p(kd), p(kv), len(kd), 1e-12, _lib_preconditioners()[fs.PCG_PRECOND], 1e-12, 100000, p(react), len(react), p(U),
                                 C.byref(force), C.byref(iters), C.byref(rel), C.byref(nnz), C.byref(msa), C.byref(mss))
     check(ctx.h, rc)
     mesh = dv.DeviceMesh.from_host(coords, n1, n2)

@@ -57,7 +57,7 @@ def main():
             hi, lo = fs.grip_nodes(coords, 1.5, 1)
             kd, kv = fs.build_bc(hi, lo, 0.02, -0.02, 1)
             sysd = dv.apply_dirichlet(ctx, K, torch.from_numpy(kd).cuda(), torch.from_numpy(kv).cuda(),
-                                      block3=(a.precond == "block3"))
+                                      precond=a.precond)
             dv.pcg(ctx, K, sysd, precond=a.precond, rtol=a.rtol, maxit=20, raise_on_maxit=False)   # warm-up
             torch.cuda.synchronize()
             t0 = time.time()
@@ -65,7 +65,7 @@ def main():
             torch.cuda.synchronize()
             dt = time.time() - t0
             tr = dv.true_residual(ctx, K, sysd, xs)
-            it_bytes = 12 * nnz + 92 * n_rows
+            it_bytes = 12 * nnz + 92 * n_rows          # CSR-sweep convention (the fused kernel streams less)
             out.update({"pcg_iters": it, "pcg_s": round(dt, 3), "us_per_iter": round(dt / max(it, 1) * 1e6, 2),
                         "iter_GBs": round(it_bytes * it / dt / 1e9, 1), "relres": rel, "true_relres": tr,
                         "precond": a.precond})
