@@ -462,10 +462,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=512)
-    ap.add_argument("--precond", default=os.environ.get("MYC_PCG_PRECOND", "block3"),
+    ap.add_argument("--precond", default=os.environ.get("MYC_PCG_PRECOND", "block6"),
                     choices=["jacobi", "block3", "block6", "block12"],
-                    help="block-Jacobi over 3x3 node blocks (default), over aligned groups of 2 / 4 nodes (block6 / block12, "
-                         "single GPU; N > 1 uses block3), or point Jacobi")
+                    help="block-Jacobi over aligned groups of 2 nodes (block6, default; single GPU -- N > 1 uses block3), "
+                         "3x3 node blocks (block3), groups of 4 nodes (block12), or point Jacobi")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-roofline", action="store_true")
     args = ap.parse_args()

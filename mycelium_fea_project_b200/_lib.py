@@ -70,6 +70,7 @@ SIGNATURES = {
     "myc_assemble_numeric": [_p, _p, _p, _p, _f64, _f64, _f64, _i64, _p, _p, _p, _p],
     "myc_apply_dirichlet": [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _f64, _p, _p, _p, _p],
     "myc_block3_inverse": [_p, _i64, _i64, _p, _p, _p, _p, _f64, _p, _p],
+    "myc_block_inverse_size": [_int, _i64],
     "myc_block_inverse_packed": [_p, _int, _i64, _i64, _p, _p, _p, _p, _f64, _p, _p],
     "myc_reduce_csr": [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _pi64, _pi64, _p],
     "myc_spmv": [_p, _i64, _p, _p, _p, _p, _p, _p],
@@ -91,7 +92,7 @@ SIGNATURES = {
     "myc_load_case_host": [_p, _p, _p, _p, _p, _i64, _i64, _f64, _f64, _f64, _p, _p, _i64, _f64, _int,
                            _f64, _i64, _p, _i64, _p, _pf64, _pi64, _pf64, _pi64, _pf64, _pf64],
 }
-_RESTYPES = {"myc_last_error": C.c_char_p, "myc_launch_count": C.c_int64}
+_RESTYPES = {"myc_last_error": C.c_char_p, "myc_launch_count": C.c_int64, "myc_block_inverse_size": C.c_int64}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here == header/library mismatch

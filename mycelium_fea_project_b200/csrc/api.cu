@@ -178,8 +178,7 @@ extern "C" int myc_load_case_host(myc_ctx* ctx, const double* h_coords, const in
     MYC_TRY(myc_block3_inverse(ctx, n_dof, 0, d_rp, d_ci, d_val, d_dinv, reg, d_binv, st));
   } else if (precond == MYC_PC_BLOCK6 || precond == MYC_PC_BLOCK12) {
     const int npb = precond == MYC_PC_BLOCK6 ? 2 : 4;
-    const int64_t R = 3 * npb;
-    MYC_TRY(myc_ensure(ctx, ctx->vec[4], (size_t)((n_dof + R - 1) / R * (R * (R + 1) / 2) + 1) * 8));
+    MYC_TRY(myc_ensure(ctx, ctx->vec[4], (size_t)(myc_block_inverse_size(npb, n_dof) + 2) * 8));
     d_binv = (double*)ctx->vec[4].p;
     MYC_TRY(myc_block_inverse_packed(ctx, npb, n_dof, 0, d_rp, d_ci, d_val, d_dinv, reg, d_binv, st));
   }

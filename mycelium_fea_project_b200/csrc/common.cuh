@@ -126,6 +126,18 @@ static inline int myc_ensure(myc_ctx* ctx, DevBuf& b, size_t bytes) {
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Doubles per block of myc_block_inverse_packed.  R = 12: symmetric-packed upper triangle (78).  R = 6: the
+// packed triangle (21), or -- build with -DMYC_BLOCK6_FULLROWS -- all six rows in full (36), so that the solver
+// reads a DOF's row with three contiguous 128-bit loads and no index arithmetic.
+#ifdef MYC_BLOCK6_FULLROWS
+#define MYC_B6_FULL 1
+#else
+#define MYC_B6_FULL 0
+#endif
+__host__ __device__ __forceinline__ constexpr int myc_block_inverse_stride(int R) {
+  return (R == 6 && MYC_B6_FULL) ? 36 : R * (R + 1) / 2;
+}
+
 // Symmetric-packed (upper triangle, row-major) position of entry (i, j) of an R x R block:
 // the layout of myc_block_inverse_packed, read back by the fused PCG kernel.
 __host__ __device__ __forceinline__ constexpr int myc_sympack(int R, int i, int j) {

@@ -245,10 +245,17 @@ block_inverse_kernel(int64_t n_blocks, int64_t n_rows, int64_t row_offset, const
         m[q + 2][q + 2] = (a00 * a11 - a01 * a10) * id;
       }
     }
-    double* out = pinv + blk * (R * (R + 1) / 2);
+    double* out = pinv + blk * myc_block_inverse_stride(R);
     for (int a = 0; a < R; ++a)
-      for (int c = a; c < R; ++c)
-        out[myc_sympack(R, a, c)] = (fr[a] && fr[c]) ? 0.5 * (m[a][c] + m[c][a]) : 0.0;
+      for (int c = a; c < R; ++c) {
+        const double e = (fr[a] && fr[c]) ? 0.5 * (m[a][c] + m[c][a]) : 0.0;
+        if (R == 6 && MYC_B6_FULL) {
+          out[a * R + c] = e;
+          out[c * R + a] = e;
+        } else {
+          out[myc_sympack(R, a, c)] = e;
+        }
+      }
   }
 }
 
@@ -325,6 +332,12 @@ extern "C" int myc_block3_inverse(myc_ctx* ctx, int64_t n_rows, int64_t row_offs
       n_rows / 3, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv, reg, d_out_binv);
   MYC_LAUNCHED(ctx);
   return MYC_OK;
+}
+
+extern "C" int64_t myc_block_inverse_size(int nodes_per_block, int64_t n_rows) {
+  if ((nodes_per_block != 2 && nodes_per_block != 4) || n_rows < 0) return -1;
+  const int R = 3 * nodes_per_block;
+  return ceil_div64(n_rows, R) * myc_block_inverse_stride(R);
 }
 
 extern "C" int myc_block_inverse_packed(myc_ctx* ctx, int nodes_per_block, int64_t n_rows, int64_t row_offset,

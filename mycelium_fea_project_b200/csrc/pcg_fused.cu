@@ -142,17 +142,19 @@ __device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoc
 }
 
 // Single-GPU barrier: every block spins on the arrive counter itself (no leader hop).
-// -DMYC_LIGHT_BARRIER (A/B build): the arrive is one release-atomic and the wait one acquire-load spin,
-// instead of __threadfence() + atomicAdd ... spin + __threadfence() (each fence compiles to
-// MEMBAR.ALL.CTA + MEMBAR.SC.GPU + ERRBAR + CCTL.IVALL).  Release covers the block's stores through the
-// preceding bar.sync (cumulativity); the acquire-load's CCTL.IVALL invalidates the SM's L1 for every warp.
+// The arrive is one release-atomic (MEMBAR.ALL.GPU + REDG) and the wait one acquire-load spin
+// (LDG.STRONG.GPU + CCTL.IVALL).  The release covers the whole block's stores through the preceding
+// bar.sync (cumulativity); the acquire-load's CCTL.IVALL invalidates the SM's L1 for every warp.
+// -DMYC_HEAVY_BARRIER restores the first form, __threadfence() + atomicAdd ... spin + __threadfence(),
+// whose fences each compile to MEMBAR.ALL.CTA + MEMBAR.SC.GPU + ERRBAR + CCTL.IVALL: measured
+// 24.39 -> 23.57 us per iteration at 512^2 (profiles/r1_block_jacobi_groups.md).
 __device__ __forceinline__ void local_barrier(const FusedArgs& a, unsigned& epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
     ++epoch;
     const unsigned target = epoch * gridDim.x;
     unsigned spins = 0;
-#ifdef MYC_LIGHT_BARRIER
+#ifndef MYC_HEAVY_BARRIER
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(&a.bar[0]), "r"(1u) : "memory");
     while (ld_acquire_gpu(&a.bar[0]) < target)
       if (++spins > FU_SPIN_LIMIT) __trap();
@@ -288,12 +290,31 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   const int g_c = lane % GR, g_first = lane - lane % GR;
   auto group_z = [&](int64_t i, double ri) -> double {    // all 32 lanes call; lanes >= GLW / i >= n idle
     const bool ok = lane < GLW && i < n;
-    const double* m = a.binv + (ok ? i / GR : 0) * (GR * (GR + 1) / 2);
     double z = 0.0;
+    if constexpr (GR == 6 && MYC_B6_FULL) {
+      // full rows: row i of its block is the six doubles at binv + 6 i (48-byte rows, 16-byte aligned)
+      double2 m01 = make_double2(0.0, 0.0), m23 = m01, m45 = m01;
+      if (ok) {
+        const double2* m = reinterpret_cast<const double2*>(a.binv + 6 * i);
+        m01 = m[0]; m23 = m[1]; m45 = m[2];
+      }
+      const int src = lane < GLW ? g_first : 0;
+      const double r0 = __shfl_sync(0xffffffffu, ri, src), r1 = __shfl_sync(0xffffffffu, ri, src + 1);
+      const double r2 = __shfl_sync(0xffffffffu, ri, src + 2), r3 = __shfl_sync(0xffffffffu, ri, src + 3);
+      const double r4 = __shfl_sync(0xffffffffu, ri, src + 4), r5 = __shfl_sync(0xffffffffu, ri, src + 5);
+      z = m01.x * r0;
+      z += m01.y * r1;
+      z += m23.x * r2;
+      z += m23.y * r3;
+      z += m45.x * r4;
+      z += m45.y * r5;
+    } else {
+      const double* m = a.binv + (ok ? i / GR : 0) * myc_block_inverse_stride(GR);
 #pragma unroll
-    for (int j = 0; j < GR; ++j) {
-      const double rj = __shfl_sync(0xffffffffu, ri, lane < GLW ? g_first + j : 0);
-      if (ok) z += m[myc_sympack(GR, g_c, j)] * rj;
+      for (int j = 0; j < GR; ++j) {
+        const double rj = __shfl_sync(0xffffffffu, ri, lane < GLW ? g_first + j : 0);
+        if (ok) z += m[myc_sympack(GR, g_c, j)] * rj;
+      }
     }
     return z;
   };
@@ -592,7 +613,7 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   *handled = 0;
   if (ctx->no_fused_pcg) return MYC_OK;
   const bool dist = ctx->world > 1;
-  if (pc >= 2 && (dist || row_offset != 0)) return MYC_OK;      // node-group blocks: single GPU only
+  if (pc >= 2 && (dist || row_offset != 0 || ((uintptr_t)d_binv & 15u) != 0)) return MYC_OK;   // node-group blocks: single GPU only
   if (dist && (!ctx->peer_ok || ctx->peer_cap < n_cols_global || ctx->world > MYC_MAX_WORLD)) return MYC_OK;
   if (!dist && n_rows == 0) return MYC_OK;
   if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;   // (same allocator on every rank)

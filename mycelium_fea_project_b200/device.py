@@ -198,7 +198,9 @@ def apply_dirichlet(ctx: Context, K: DeviceCSR, known_dofs: torch.Tensor, known_
     elif precond in ("block6", "block12"):
         npb = 2 if precond == "block6" else 4
         R = 3 * npb
-        binv = torch.empty(((K.n_rows + R - 1) // R, R * (R + 1) // 2), dtype=torch.float64, device=ctx.device)
+        n_blocks = (K.n_rows + R - 1) // R
+        size = int(lib.myc_block_inverse_size(npb, K.n_rows))          # the layout belongs to the library
+        binv = torch.empty((n_blocks, size // n_blocks if n_blocks else 0), dtype=torch.float64, device=ctx.device)
         check(ctx.h, lib.myc_block_inverse_packed(ctx.h, npb, K.n_rows, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx),
                                                   _ptr(K.val), _ptr(dinv), float(reg), _ptr(binv), _stream()))
     return DirichletSystem(ubc, rhs, dinv, binv, float(reg), precond if binv is not None else None)

@@ -51,7 +51,7 @@ PCG_RTOL = 1e-10
 PCG_MAXIT = 500_000
 # "jacobi" (point), "block3" (3x3 node blocks), "block6" / "block12" (aligned blocks of 2 / 4 consecutive
 # nodes; single GPU).  MYC_PCG_PRECOND overrides the default.
-PCG_PRECOND = os.environ.get("MYC_PCG_PRECOND", "block3")
+PCG_PRECOND = os.environ.get("MYC_PCG_PRECOND", "block6")
 
 
 def _ctx():

@@ -23,6 +23,7 @@ kd, kv = fs.build_bc(hi, lo, 0.02, -0.02, 1)
 res = fs.analyze_load_case(mesh, kd, kv, react_dofs=3 * hi + 1, rtol=1e-10)
 torch.cuda.synchronize()
 n, nnz, its = res.K.n_rows, res.K.nnz, res.iterations
-alg = (its + 1) * (52 / 9 * nnz + 20 * n) + its * 120 * n
-print(f"ok grid={N} n_dof={n} nnz={nnz} iterations={its} relres={res.relres:.3e} force={res.total_force:.6e} "
+vec = {"jacobi": 96, "block3": 120, "block6": 124, "block12": 148}[fs.PCG_PRECOND]   # B per row per iteration
+alg = (its + 1) * (52 / 9 * nnz + 20 * n) + its * vec * n
+print(f"ok precond={fs.PCG_PRECOND} grid={N} n_dof={n} nnz={nnz} iterations={its} relres={res.relres:.3e} force={res.total_force:.6e} "
       f"algorithmic_bytes_per_launch={alg:.6e} ms_solve={res.ms_solve:.2f}")
