@@ -144,8 +144,8 @@ int myc_block3_inverse(myc_ctx* ctx, int64_t n_rows, int64_t row_offset, const i
  * nodes_per_block (2 or 4) consecutive nodes -- R = 3*nodes_per_block rows -- of K + reg*I, rows/cols
  * of known DOFs (and the padding of a ragged last block) zeroed; a block that is singular in floating
  * point (coincident nodes coupled with ~1e28) keeps the inverses of its 3x3 node blocks only.  The layout
- * of d_out_pinv belongs to the library (symmetric-packed upper triangles: block b at b*R(R+1)/2, entry
- * (i <= j) at i*R - i(i-1)/2 + (j-i); a -DMYC_BLOCK6_FULLROWS build stores the 6x6 blocks row by row):
+ * of d_out_pinv belongs to the library (6x6 blocks row by row, 36 doubles each; 12x12 blocks as
+ * symmetric-packed upper triangles, entry (i <= j) at i*R - i(i-1)/2 + (j-i), 78 doubles each):
  * allocate myc_block_inverse_size(nodes_per_block, n_rows) doubles and pass the buffer to myc_pcg_solve
  * unchanged.  Single GPU (row_offset must be a multiple of R). */
 int64_t myc_block_inverse_size(int nodes_per_block, int64_t n_rows);

@@ -126,13 +126,14 @@ static inline int myc_ensure(myc_ctx* ctx, DevBuf& b, size_t bytes) {
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// Doubles per block of myc_block_inverse_packed.  R = 12: symmetric-packed upper triangle (78).  R = 6: the
-// packed triangle (21), or -- build with -DMYC_BLOCK6_FULLROWS -- all six rows in full (36), so that the solver
-// reads a DOF's row with three contiguous 128-bit loads and no index arithmetic.
-#ifdef MYC_BLOCK6_FULLROWS
-#define MYC_B6_FULL 1
-#else
+// Doubles per block of myc_block_inverse_packed.  R = 12: symmetric-packed upper triangle (78).  R = 6: all
+// six rows in full (36), so that the solver reads a DOF's row with three contiguous 128-bit loads and no
+// index arithmetic (measured 25.66 -> 24.61 us per iteration at 512^2 against the packed triangle, which
+// -DMYC_BLOCK6_PACKED restores: 21 doubles).
+#ifdef MYC_BLOCK6_PACKED
 #define MYC_B6_FULL 0
+#else
+#define MYC_B6_FULL 1
 #endif
 __host__ __device__ __forceinline__ constexpr int myc_block_inverse_stride(int R) {
   return (R == 6 && MYC_B6_FULL) ? 36 : R * (R + 1) / 2;

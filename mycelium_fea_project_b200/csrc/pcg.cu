@@ -328,9 +328,9 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
         const double mat = op_used == 2 ? (52.0 / 9.0) * h_nnz : 12.0 * h_nnz;
         ctx->prof_bytes += ((double)fin.iters + 1.0) * (mat + 20.0 * (double)n_rows) +
                            (double)fin.iters * (double)n_rows *           // + the inverse blocks of the preconditioner
-                               (precond == MYC_PC_BLOCK12 ? 96.0 + 8.0 * myc_block_inverse_stride(12) / 12.0
-                                : precond == MYC_PC_BLOCK6 ? 96.0 + 8.0 * myc_block_inverse_stride(6) / 6.0
-                                : block3 ? 120.0 : 96.0);
+                               // algorithmic minimum: the symmetric inverse, R(R+1)/2 doubles per R rows
+                               // (the 6x6 blocks are STORED row by row, 48 B per row; not counted)
+                               (precond == MYC_PC_BLOCK12 ? 148.0 : precond == MYC_PC_BLOCK6 ? 124.0 : block3 ? 120.0 : 96.0);
         ctx->prof_op = op_used;
       }
       if (h_out_iters) *h_out_iters = (int64_t)fin.iters;

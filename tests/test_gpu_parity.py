@@ -326,7 +326,7 @@ def test_block_inverse_packed_matches_numpy(ctx, precond, R):
     n = K.n_rows
     n_blocks = (n + R - 1) // R
     P = sysd.binv.cpu().numpy()
-    full_rows = P.shape[1] == R * R          # a -DMYC_BLOCK6_FULLROWS build stores the 6x6 blocks row by row
+    full_rows = P.shape[1] == R * R          # 6x6 blocks are stored row by row (packed with -DMYC_BLOCK6_PACKED)
     assert P.shape == (n_blocks, R * R if full_rows else R * (R + 1) // 2)
     Ks = K.to_scipy().tocsr()
     known = np.zeros(n, bool)
