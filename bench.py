@@ -350,8 +350,18 @@ def run_ours(args):
                  "for jacobi|block3|block6|block12, "
                  "i.e. what this kernel has to stream -- 12 nnz instead of 52/9 nnz if MYC_NO_SYM3=1)") if fused else \
             "myc_spmv_tma_kernel<EpiCgAp> (Ap = K p + reg p, fused p.Ap; every 32nd launch sampled)"
+        # DRAM traffic of one launch from the committed ncu --set full captures of this workload's Y load case
+        # (profiles/r1_fused_solve_ncu.md): static, only quoted for the configuration that was captured
+        captured = {"block6": (8.0532e10, 6146), "block3": (7.2638e10, 7292)}
+        traffic = traffic_src = None
+        if fused and world == 1 and args.grid == 512 and args.precond in captured:
+            traffic, cap_its = captured[args.precond]
+            traffic_src = (f"ncu --set full capture of one Y-load-case launch ({cap_its} iterations): dram read + write per "
+                           f"launch = {traffic / cap_its / 1e6:.1f} MB per iteration against ~108 MB algorithmic -- the 512^2 "
+                           "working set stays in L2 (hit rate 86-88 %); profiles/r1_fused_solve_ncu.md; static, not re-measured here")
         roof = {"bound": "hbm", "kernel": kname,
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "avg_launch_us": spmv_ms / spmv_n * 1e3, "launches_sampled": spmv_n,
                 "algorithmic_bytes_per_launch": spmv_bytes / spmv_n,
                 "share_of_step": (spmv_ms / ms_total if fused else (prof[3] * spmv_ms / spmv_n) / ms_total) if ms_total else None,
