@@ -165,3 +165,26 @@ def test_petsc_style_c_port_agrees_with_direct_solve(golden_dir):
     # PETSc's residual is relative to a b that contains the prescribed values, so the free part is
     # resolved less tightly than rtol suggests
     assert np.linalg.norm(U - g["U"]) <= 1e-6 * np.linalg.norm(g["U"])
+
+
+@pytest.mark.parametrize("rows_per_block", [3, 6, 12])
+def test_block_jacobi_checker_agrees_with_direct_solve(rows_per_block, golden_dir):
+    """oracle.block_jacobi_pcg (the checker of the CUDA path's block preconditioners) solves the
+    reduced system of src/fea_solver.py:118-125 to the same U_f as spsolve, in fewer iterations the
+    larger the aligned blocks are; its block inverses are exact and symmetric."""
+    g = np.load(os.path.join(golden_dir, "solve_synth64.npz"))
+    from mycelium_fea_project_b200.synth import synth_network
+    coords, n1, n2 = synth_network(64)
+    K = fo.assemble_global_stiffness(coords, n1, n2, np.ones(len(n1), bool))
+    free, K_ff, F_f = fo.reduce_system(K, g["known_dofs"], g["known_vals"])
+    x, it, rel = fo.block_jacobi_pcg(K_ff, F_f, free, rows_per_block, rtol=1e-12)
+    ref = g["U"][free]
+    assert rel <= 1e-12
+    assert np.linalg.norm(x - ref) <= 1e-8 * np.linalg.norm(ref)
+    _, it_point, _ = fo.jacobi_pcg(K_ff.tocsr(), F_f, rtol=1e-12)
+    assert it < it_point
+    labels, blocks = fo.aligned_block_inverses(K_ff, free, rows_per_block)
+    assert len(blocks) == len(np.unique(labels))
+    idx, inv = next(iter(blocks.values()))
+    assert np.allclose(inv, inv.T, rtol=1e-10, atol=0.0) or inv.shape == (1, 1)
+    assert np.allclose(inv @ K_ff.tocsr()[idx][:, idx].toarray(), np.eye(len(idx)), atol=1e-8)
