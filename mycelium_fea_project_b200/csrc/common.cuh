@@ -32,6 +32,7 @@ struct myc_ctx {
   bool no_block3_spmv = false;     // MYC_NO_BLOCK3_SPMV=1: ignore the node-block hint
   bool no_sym3 = false;            // MYC_NO_SYM3=1: the fused PCG streams the CSR, not the symmetric block view
   bool no_halo_overlap = true;     // MYC_HALO_OVERLAP=1 enables the gated sweep (halo waits inside the sweep)
+  bool dist_block6 = false;        // MYC_DIST_BLOCK6=1: 6x6 Jacobi blocks in the multi-GPU solver kernel (caller aligns the cuts)
   bool asm_direct_fill = false;    // MYC_ASM_DIRECT_FILL=1: numeric assembly stores rows straight to global memory (no staging)
   bool csr_block3 = false;         // caller's hint: the CSR it passes has the 3x3 node-block structure
 

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   constexpr bool BLOCK3 = PC == 1;
   constexpr int GR = PC == 2 ? 6 : 12;                 // rows per block of the node-group preconditioners
   constexpr int GLW = (32 / GR) * GR;                  // lanes of a warp that carry rows: 30 (GR 6), 24 (GR 12)
-  static_assert(PC >= 0 && PC <= 3 && !(DIST && PC >= 2), "node-group blocks are single-GPU");
+  static_assert(PC >= 0 && PC <= 3 && !(DIST && PC == 3), "12x12 blocks are single-GPU");
   using Cfg = std::conditional_t<OP == 1, TmCfgBlock3, TmCfgGeneric>;
   using Pipe = std::conditional_t<OP == 2, TmSymPipe, TmPipe>;
   extern __shared__ __align__(128) unsigned char fu_smem[];
@@ -589,18 +589,20 @@ extern "C" int myc_dist_peer_open(myc_ctx* ctx, const uint8_t* h_handles) {
 namespace {
 template <int PC, int OP, bool DIST>
 const void* fused_fn() { return (const void*)pcg_fused_kernel<PC, OP, DIST>; }
-constexpr int FU_VARIANTS = 18;
-// index = dist*6 + op*2 + pc for pc 0 / 1;  12 + op*2 + (pc - 2) for the single-GPU node-group blocks
+constexpr int FU_VARIANTS = 21;
+// index = dist*6 + op*2 + pc for pc 0 / 1;  12 + op*2 + (pc - 2) for the single-GPU node-group blocks;
+// 18 + op for the 6x6 blocks on several GPUs (rank boundaries on even nodes, MYC_DIST_BLOCK6=1)
 const void* fused_variant(int idx) {
   static const void* tab[FU_VARIANTS] = {
       fused_fn<0, 0, false>(), fused_fn<1, 0, false>(), fused_fn<0, 1, false>(), fused_fn<1, 1, false>(),
       fused_fn<0, 2, false>(), fused_fn<1, 2, false>(), fused_fn<0, 0, true>(),  fused_fn<1, 0, true>(),
       fused_fn<0, 1, true>(),  fused_fn<1, 1, true>(),  fused_fn<0, 2, true>(),  fused_fn<1, 2, true>(),
       fused_fn<2, 0, false>(), fused_fn<3, 0, false>(), fused_fn<2, 1, false>(), fused_fn<3, 1, false>(),
-      fused_fn<2, 2, false>(), fused_fn<3, 2, false>()};
+      fused_fn<2, 2, false>(), fused_fn<3, 2, false>(),
+      fused_fn<2, 0, true>(),  fused_fn<2, 1, true>(),  fused_fn<2, 2, true>()};
   return tab[idx];
 }
-int fused_variant_op(int idx) { return (idx % 6) / 2; }
+int fused_variant_op(int idx) { return idx >= 18 ? idx - 18 : (idx % 6) / 2; }
 size_t fused_smem(int op) {
   return op == 2 ? tm_sym_smem_bytes(FU_WARPS) : tm_smem_bytes(FU_WARPS, op == 1 ? TmCfgBlock3::CAP : TmCfgGeneric::CAP);
 }
@@ -613,7 +615,10 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   *handled = 0;
   if (ctx->no_fused_pcg) return MYC_OK;
   const bool dist = ctx->world > 1;
-  if (pc >= 2 && (dist || row_offset != 0 || ((uintptr_t)d_binv & 15u) != 0)) return MYC_OK;   // node-group blocks: single GPU only
+  // node-group blocks: rows of a block must be rank-local; on several GPUs only the 6x6 blocks, opt-in
+  if (pc >= 2 && (row_offset % (pc == 2 ? 6 : 12) != 0 || ((uintptr_t)d_binv & 15u) != 0 ||
+                  (dist && (pc != 2 || !ctx->dist_block6))))
+    return MYC_OK;
   if (dist && (!ctx->peer_ok || ctx->peer_cap < n_cols_global || ctx->world > MYC_MAX_WORLD)) return MYC_OK;
   if (!dist && n_rows == 0) return MYC_OK;
   if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;   // (same allocator on every rank)
@@ -711,7 +716,8 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
     a.peer_sync[0] = nullptr;
   }
   void* params[] = {&a};
-  const void* fn = pc >= 2 ? fused_variant(12 + op * 2 + (pc - 2)) : fused_variant((dist ? 6 : 0) + op * 2 + (pc == 1 ? 1 : 0));
+  const void* fn = pc >= 2 ? (dist ? fused_variant(18 + op) : fused_variant(12 + op * 2 + (pc - 2)))
+                           : fused_variant((dist ? 6 : 0) + op * 2 + (pc == 1 ? 1 : 0));
   MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FU_THREADS), params, fused_smem(op), st));
   ctx->launches++;
   *handled = 1;

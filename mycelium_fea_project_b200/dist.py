@@ -25,13 +25,21 @@ import numpy as np
 # ---------------------------------------------------------------------------------------------
 # plan (pure numpy -- no CUDA, no torch)
 # ---------------------------------------------------------------------------------------------
-def partition_nodes(n_nodes: int, world: int) -> np.ndarray:
+def partition_nodes(n_nodes: int, world: int, align: int = 1) -> np.ndarray:
     """Balanced contiguous node ranges: offsets[world+1] (first n_nodes % world ranks get one more,
-    PETSC_DECIDE's rule applied to nodes instead of rows)."""
-    base, rem = divmod(int(n_nodes), int(world))
-    sizes = np.full(world, base, dtype=np.int64)
-    sizes[:rem] += 1
-    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    PETSC_DECIDE's rule applied to nodes instead of rows).  ``align`` > 1 puts every interior cut on a
+    multiple of ``align`` nodes (the aligned block-Jacobi groups must not straddle ranks); the balance
+    rule is then applied to groups of ``align`` nodes and the last rank takes the ragged tail."""
+    n_nodes, world, align = int(n_nodes), int(world), int(align)
+    if align <= 1:
+        base, rem = divmod(n_nodes, world)
+        sizes = np.full(world, base, dtype=np.int64)
+        sizes[:rem] += 1
+        return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    groups = -(-n_nodes // align)
+    off = np.minimum(partition_nodes(groups, world) * align, n_nodes)
+    off[-1] = n_nodes
+    return off.astype(np.int64)
 
 
 def owner_of(nodes, offsets):
@@ -87,12 +95,12 @@ class HaloPlan:
         return int(self.offsets[self.rank + 1])
 
 
-def make_plan(n1, n2, active, n_nodes, rank, world, all_gather=None) -> HaloPlan:
+def make_plan(n1, n2, active, n_nodes, rank, world, all_gather=None, align=1) -> HaloPlan:
     """Build this rank's plan.  ``all_gather(array) -> list of arrays`` exchanges the need
     table between ranks (torch.distributed in production); if None, every rank's needs are
     computed locally (all ranks hold the whole mesh, so this is equivalent, just O(world) more
     host work)."""
-    offsets = partition_nodes(n_nodes, world)
+    offsets = partition_nodes(n_nodes, world, align)
     lo, hi = halo_ranges(n1, n2, active, offsets, rank)
     if all_gather is not None:
         table = all_gather(np.stack([lo, hi]))
@@ -143,7 +151,12 @@ class DistributedSolver:
             dist.all_gather_object(out, arr)
             return out
 
-        self.plan = make_plan(n1, n2, active, self.n_nodes, self.rank, self.world, all_gather)
+        # MYC_DIST_BLOCK6=1 (opt-in, not yet measured on N > 1 GPUs): cuts on even nodes so that the 6x6
+        # Jacobi blocks stay rank-local and "block6" can run in the multi-GPU solver kernel too
+        import os
+        self.block6 = os.environ.get("MYC_DIST_BLOCK6") == "1"
+        self.plan = make_plan(n1, n2, active, self.n_nodes, self.rank, self.world, all_gather,
+                              align=2 if self.block6 else 1)
         self.mesh = dv.DeviceMesh.from_host(coords, n1, n2, active, device=self.ctx.device)
         if self.world > 1 and self.ctx.world == 1:
             path = nccl_library_path().encode()
@@ -225,9 +238,9 @@ class DistributedSolver:
         self._install_plan()
         td = lambda a, dt: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
         kd, kv = td(known_dofs, np.int64), td(known_vals, np.float64)
-        if precond in ("block6", "block12"):
-            # the node-group blocks live in the single-GPU solver kernel only (rank boundaries are not
-            # aligned to node groups): a row-partitioned solve uses the 3x3 node blocks
+        if precond == "block12" or (precond == "block6" and not (self.block6 and K.row_offset % 6 == 0)):
+            # the node-group blocks need rank boundaries aligned to the groups: without MYC_DIST_BLOCK6=1
+            # a row-partitioned solve uses the 3x3 node blocks
             precond = "block3"
         sysd = dv.apply_dirichlet(ctx, K, kd, kv, reg, precond=precond)
         self._ensure_peer(K.n_cols)

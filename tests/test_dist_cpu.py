@@ -43,6 +43,30 @@ def test_partition_and_plan_single_process():
                 assert p.give_lo[q] == pq.need_lo[r] and p.give_hi[q] == pq.need_hi[r]
 
 
+def test_aligned_partition_keeps_node_pairs_on_one_rank():
+    """MYC_DIST_BLOCK6 layout: every interior cut on an even node (or at the end), still balanced."""
+    for n, world in [(10, 3), (11, 4), (174738, 8), (7, 8), (2, 4), (0, 2), (1067, 2), (1, 1)]:
+        off = md.partition_nodes(n, world, align=2)
+        assert off[0] == 0 and off[-1] == n and np.all(np.diff(off) >= 0)
+        assert np.all((off[1:-1] % 2 == 0) | (off[1:-1] == n))
+        if n >= 4 * world:
+            assert np.diff(off).max() - np.diff(off).min() <= 2
+        assert np.array_equal(md.partition_nodes(n, world, align=1), md.partition_nodes(n, world))
+    coords, n1, n2 = synth_network(24)
+    n = len(coords)
+    for r in range(3):
+        p = md.make_plan(n1, n2, None, n, r, 3, align=2)
+        assert p.node_begin % 2 == 0
+        # halo ranges still cover every remote neighbour of the rank's own nodes
+        b, e = p.node_begin, p.node_end
+        far = np.concatenate([n2[(n1 >= b) & (n1 < e)], n1[(n2 >= b) & (n2 < e)]])
+        far = far[(far < b) | (far >= e)]
+        own = md.owner_of(far, p.offsets)
+        for q in np.unique(own):
+            f = far[own == q]
+            assert p.need_lo[q] <= f.min() and f.max() < p.need_hi[q]
+
+
 def test_locality_order_makes_ranges_small():
     coords, n1, n2 = synth_network(32)
     rng = np.random.default_rng(0)
