@@ -233,7 +233,15 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   if constexpr (OP == 2) tm_sym_pipe_init(pp, fu_smem, FU_WARPS, warp, lane);
   else tm_pipe_init(pp, fu_smem, FU_WARPS, warp, lane, Cfg::CAP);
   const int32_t nnz_total = a.rp[n];
+  // Global warp number: tiles (and the vector pass's row chunks) are dealt round-robin over it.  Block-major
+  // numbering gives the last, partial round to the first blocks only: at 512^2, 17,474 tiles over 4,736 warps
+  // = 4 tiles per warp in blocks 0..101 and 3 in blocks 103..147.  -DMYC_BLOCK_FASTEST_WARPS numbers the warps
+  // block-fastest so that every SM gets the same share of the partial round (A/B build, not measured yet).
+#ifdef MYC_BLOCK_FASTEST_WARPS
+  const int64_t gw = (int64_t)warp * gridDim.x + blockIdx.x;
+#else
   const int64_t gw = (int64_t)blockIdx.x * FU_WARPS + warp;
+#endif
   const int64_t n_warps = (int64_t)gridDim.x * FU_WARPS;
 
   // store one entry of u locally and into every GPU that gathers it
