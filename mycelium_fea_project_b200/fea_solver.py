@@ -52,6 +52,8 @@ PCG_MAXIT = 500_000
 # "jacobi" (point), "block3" (3x3 node blocks), "block6" / "block12" (aligned blocks of 2 / 4 consecutive
 # nodes; single GPU).  MYC_PCG_PRECOND overrides the default.
 PCG_PRECOND = os.environ.get("MYC_PCG_PRECOND", "block6")
+if PCG_PRECOND not in ("jacobi", "block3", "block6", "block12"):
+    raise ValueError(f"MYC_PCG_PRECOND={PCG_PRECOND!r}: expected jacobi, block3, block6 or block12")
 
 
 def _ctx():
