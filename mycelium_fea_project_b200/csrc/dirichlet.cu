@@ -177,6 +177,7 @@ block3_kernel(int64_t n_nodes_local, int64_t row_offset, const int32_t* __restri
 // rows and columns by identity, invert in place by Gauss-Jordan (the block is a principal submatrix
 // of K_ff + reg I, hence SPD: no pivoting needed), store the symmetrised upper triangle.  A block
 // that is singular in floating point keeps only the inverses of its 3x3 node blocks.
+// [host-test-begin block_inverse_kernel]  (tests/test_kernel_logic_host.py compiles this text with g++)
 template <int R>
 __global__ void __launch_bounds__(128)
 block_inverse_kernel(int64_t n_blocks, int64_t n_rows, int64_t row_offset, const int32_t* __restrict__ rp,
@@ -258,6 +259,7 @@ block_inverse_kernel(int64_t n_blocks, int64_t n_rows, int64_t row_offset, const
       }
   }
 }
+// [host-test-end block_inverse_kernel]
 
 }  // namespace
 
