@@ -23,6 +23,7 @@
 
 namespace {
 
+// [host-test-begin assembly_kernels]  (tests/test_kernel_logic_host.py compiles this text with g++)
 constexpr int AS_THREADS = 256;
 
 __device__ __forceinline__ bool owned(int32_t node, int64_t nb, int64_t ne) {
@@ -179,6 +180,8 @@ fill_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ eval
     fill_node(keys, evals, es, ee, w, nb + i, dmask, coords, n1, n2, bc, col_idx, val, 9 * (int64_t)bs);
   }
 }
+
+// [host-test-end assembly_kernels]
 
 // Staged form (default).  The rows of 32 consecutive nodes occupy ONE contiguous window of col_idx / val
 // (9 * block_start[first] .. 9 * block_start[last + 1]), so a warp builds the window in shared memory

@@ -20,3 +20,4 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline int atomicAdd(int* p, int v) { const int old = *p; *p += v; return old; }
