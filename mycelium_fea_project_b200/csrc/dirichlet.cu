@@ -8,6 +8,7 @@
 
 namespace {
 
+// [host-test-begin dirichlet_kernels]  (tests/test_kernel_logic_host.py compiles this text with g++)
 constexpr int DI_THREADS = 256;
 
 __global__ void __launch_bounds__(DI_THREADS)
@@ -44,6 +45,8 @@ jacobi_kernel(int64_t n_rows, int64_t row_offset, const int32_t* __restrict__ rp
     dinv[i] = 1.0 / (d + reg);
   }
 }
+
+// [host-test-end dirichlet_kernels]
 
 struct EpiRhs {   // b = -(K u_bc) on free rows, 0 on known rows
   static constexpr int NACC = 0;

@@ -7,6 +7,7 @@
 
 namespace {
 
+// [host-test-begin strain_kernel]  (tests/test_kernel_logic_host.py compiles this text with g++)
 constexpr int ST_THREADS = 256;
 
 __global__ void __launch_bounds__(ST_THREADS)
@@ -39,6 +40,8 @@ strain_kernel(const double* __restrict__ coords, const int32_t* __restrict__ n1,
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
   if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_active, cnt);
 }
+
+// [host-test-end strain_kernel]
 
 }  // namespace
 

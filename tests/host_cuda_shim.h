@@ -21,3 +21,6 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline int atomicAdd(int* p, int v) { const int old = *p; *p += v; return old; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long old = *p; *p += v; return old; }
+// the one emulated thread already holds the whole grid's partial: every other lane of a warp reduction contributes zero
+template <class T> static inline T __shfl_down_sync(unsigned, T, int) { return T(0); }
