@@ -37,6 +37,7 @@ __host__ __device__ constexpr size_t tm_sym_smem_bytes(int warps) {
   return warps * tm_sym_smem_per_warp() + warps * TM_STAGES * sizeof(uint64_t) + 128;
 }
 
+// [host-test-begin sym3_convert]  (tests/test_kernel_logic_host.py compiles this text with g++)
 // One thread per owned node: pack the node's blocks.  rp/ci/v: node-block-structured CSR (local rows).
 // bval: 6 doubles per block (xx xy xz yy yz zz), bcol: DOF column of the block's first entry.
 // *bad is raised if a block is not bitwise symmetric (then the caller keeps using the CSR sweep).
@@ -60,6 +61,8 @@ myc_sym3_convert_kernel(int64_t n_nodes, const int32_t* __restrict__ rp, const i
     }
   }
 }
+
+// [host-test-end sym3_convert]
 
 // Per-warp pipeline state for the sym3 ring (same shape as TmPipe).
 struct TmSymPipe {
