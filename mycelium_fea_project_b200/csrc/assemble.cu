@@ -75,6 +75,33 @@ edge_emit_kernel(const int32_t* __restrict__ n1, const int32_t* __restrict__ n2,
   }
 }
 
+// Short sort (MYC_ASM_SHORT_SORT=1): the radix passes cover the source-node bits only, so a node's segment
+// arrives in emission (= element) order; this kernel orders it by destination node with a stable insertion
+// sort -- the same permutation the full-key sort produces, at O(degree^2) per node (degree <= ~6 on hyphal
+// networks; a hub of degree d costs d^2/2 moves in one thread, which is why the full sort stays the default).
+__global__ void __launch_bounds__(AS_THREADS)
+segment_order_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, const int32_t* __restrict__ edge_start,
+                     int64_t n_local, int dst_bits) {
+  const uint64_t dmask = ((uint64_t)1 << dst_bits) - 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t es = edge_start[i], ee = edge_start[i + 1];
+    for (int32_t k = es + 1; k < ee; ++k) {
+      const uint64_t kk = keys[k];
+      const uint32_t vv = vals[k];
+      const uint64_t d = kk & dmask;
+      int32_t j = k - 1;
+      while (j >= es && (keys[j] & dmask) > d) {       // strictly greater: equal destinations keep element order
+        keys[j + 1] = keys[j];
+        vals[j + 1] = vals[j];
+        --j;
+      }
+      keys[j + 1] = kk;
+      vals[j + 1] = vv;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(AS_THREADS)
 block_count_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ edge_start,
                    int64_t n_local, int64_t nb, int dst_bits, int32_t* __restrict__ bc) {
@@ -298,10 +325,15 @@ extern "C" int myc_assemble_symbolic(myc_ctx* ctx, const int32_t* d_n1, const in
                                                     dst_bits, cnt, (uint64_t*)ctx->sort_keys[0].p,
                                                     (uint32_t*)ctx->sort_vals[0].p, deg);
     MYC_LAUNCHED(ctx);
-    MYC_TRY(myc_radix_sort_pairs(ctx, n_edges, key_bits, &sorted, st));
+    MYC_TRY(myc_radix_sort_pairs(ctx, n_edges, ctx->asm_short_sort ? dst_bits : 0, key_bits, &sorted, st));
   }
   // per-node segments of the sorted stream
   MYC_TRY(myc_exclusive_scan_i32(ctx, deg, deg, n_local, true, nullptr, st));
+  if (ctx->asm_short_sort && n_edges > 0 && n_local > 0) {
+    segment_order_kernel<<<g_node, AS_THREADS, 0, st>>>((uint64_t*)ctx->sort_keys[sorted].p,
+                                                        (uint32_t*)ctx->sort_vals[sorted].p, deg, n_local, dst_bits);
+    MYC_LAUNCHED(ctx);
+  }
   if (n_local > 0) {
     block_count_kernel<<<g_node, AS_THREADS, 0, st>>>((const uint64_t*)ctx->sort_keys[sorted].p, deg,
                                                       n_local, node_begin, dst_bits, nbc);

@@ -33,6 +33,7 @@ struct myc_ctx {
   bool no_sym3 = false;            // MYC_NO_SYM3=1: the fused PCG streams the CSR, not the symmetric block view
   bool no_halo_overlap = true;     // MYC_HALO_OVERLAP=1 enables the gated sweep (halo waits inside the sweep)
   bool dist_block6 = false;        // MYC_DIST_BLOCK6=1: 6x6 Jacobi blocks in the multi-GPU solver kernel (caller aligns the cuts)
+  bool asm_short_sort = false;     // MYC_ASM_SHORT_SORT=1: radix passes over the source-node bits only + per-node neighbour ordering
   bool asm_direct_fill = false;    // MYC_ASM_DIRECT_FILL=1: numeric assembly stores rows straight to global memory (no staging)
   bool csr_block3 = false;         // caller's hint: the CSR it passes has the 3x3 node-block structure
 
@@ -160,9 +161,9 @@ static inline int grid_for(const myc_ctx* ctx, int64_t n_tiles, int blocks_per_s
 // write_total_at_end is set (CSR-style offsets), truncated to int32 (caller checks d_total).
 int myc_exclusive_scan_i32(myc_ctx* ctx, const int32_t* d_in, int32_t* d_out, int64_t n,
                            bool write_total_at_end, int64_t* d_total, cudaStream_t st);
-// radix_sort.cu: stable LSD sort of (key64, val32) pairs on the low `key_bits` bits.
+// radix_sort.cu: stable LSD sort of (key64, val32) pairs on key bits [start_bit, key_bits).
 // Returns the index (0/1) of the ping-pong buffer holding the result.
-int myc_radix_sort_pairs(myc_ctx* ctx, int64_t n, int key_bits, int* out_buf, cudaStream_t st);
+int myc_radix_sort_pairs(myc_ctx* ctx, int64_t n, int start_bit, int key_bits, int* out_buf, cudaStream_t st);
 
 // spmv.cu
 int myc_launch_spmv(myc_ctx* ctx, int64_t n_rows, const int32_t* rp, const int32_t* ci,

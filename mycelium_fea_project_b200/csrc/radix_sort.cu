@@ -94,17 +94,18 @@ rs_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restri
 
 }  // namespace
 
-int myc_radix_sort_pairs(myc_ctx* ctx, int64_t n, int key_bits, int* out_buf, cudaStream_t st) {
-  // input pairs are in sort_keys[0] / sort_vals[0]; both ping-pong buffers must hold n items
+int myc_radix_sort_pairs(myc_ctx* ctx, int64_t n, int start_bit, int key_bits, int* out_buf, cudaStream_t st) {
+  // input pairs are in sort_keys[0] / sort_vals[0]; both ping-pong buffers must hold n items.
+  // Sorts on key bits [start_bit, key_bits); stable, so the order on the lower bits is the input order.
   *out_buf = 0;
-  if (n <= 1 || key_bits <= 0) return MYC_OK;
+  if (n <= 1 || key_bits <= start_bit) return MYC_OK;
   if (n >= (int64_t)1 << 31) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "radix sort: %lld items exceed int32 offsets", (long long)n);
   const int64_t n_tiles = ceil_div64(n, RS_TILE);
   MYC_TRY(myc_ensure(ctx, ctx->sort_table, (size_t)(n_tiles * RS_RADIX + 1) * sizeof(int32_t)));
   int32_t* table = (int32_t*)ctx->sort_table.p;
   const int grid = grid_for(ctx, n_tiles, 4);
   int cur = 0;
-  for (int shift = 0; shift < key_bits; shift += 8) {
+  for (int shift = start_bit; shift < key_bits; shift += 8) {
     const uint64_t* kin = (const uint64_t*)ctx->sort_keys[cur].p;
     const uint32_t* vin = (const uint32_t*)ctx->sort_vals[cur].p;
     uint64_t* kout = (uint64_t*)ctx->sort_keys[cur ^ 1].p;

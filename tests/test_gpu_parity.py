@@ -189,6 +189,22 @@ def test_assembly_staged_fill_matches_direct_fill(monkeypatch):
         ctx2.close()
 
 
+@pytest.mark.skipif(os.environ.get("MYC_TEST_SHORT_SORT") != "1",
+                    reason="opt-in: MYC_ASM_SHORT_SORT=1 (radix passes over the source bits only) has not run on a GPU yet")
+def test_assembly_short_sort_opt_in(monkeypatch):
+    """Same CSR, bit for bit, as the full-key sort (logic checked on the CPU in test_kernel_logic_host.py)."""
+    coords, n1, n2 = synth_network(128, seed=7)
+    act = np.random.default_rng(7).random(len(n1)) > 0.2
+    ref = fs.assemble_global_stiffness(coords, (n1, n2), act)
+    monkeypatch.setenv("MYC_ASM_SHORT_SORT", "1")
+    ctx2 = dv.Context(0)
+    try:
+        K = dv.assemble(ctx2, dv.DeviceMesh.from_host(coords, n1, n2, act), fs.E_mod, fs.A, fs.I).to_scipy()
+    finally:
+        ctx2.close()
+    assert np.array_equal(K.indptr, ref.indptr) and np.array_equal(K.indices, ref.indices) and np.array_equal(K.data, ref.data)
+
+
 def test_assembly_row_block_is_slice_of_global(ctx):
     """Multi-GPU layout: a rank's rows are a verbatim slice of the global CSR."""
     coords, n1, n2 = synth_network(64)
