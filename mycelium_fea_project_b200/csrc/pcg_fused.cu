@@ -115,6 +115,32 @@ __device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoc
                                               F&& leader_work) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
+#ifdef MYC_LIGHT_DIST_BARRIER
+  // A/B build (not measured yet): the same release/acquire chain with the redundant fences removed, as in
+  // local_barrier.  arrive = acq_rel atomic (releases this block's stores, and lets the last arriver acquire
+  // everybody's); blocks that stored into a peer GPU still issue the system-scope fence first; the leader
+  // publishes with st.release, the others wake on ld.acquire (whose CCTL.IVALL invalidates L1).
+  if (threadIdx.x == 0) {
+    ++epoch;
+    if (sys_release) __threadfence_system();
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(&a.bar[0]), "r"(1u) : "memory");
+    *s_leader = (old == epoch * gridDim.x - 1u);
+  }
+  __syncthreads();
+  if (*s_leader && warp == 0) {
+    __syncwarp();
+    leader_work(lane);
+    __syncwarp();
+    if (lane == 0) st_release_gpu(&a.bar[1], epoch);
+  }
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    while (ld_acquire_gpu(&a.bar[1]) < epoch)
+      if (++spins > FU_SPIN_LIMIT) __trap();
+  }
+  __syncthreads();
+#else
   if (threadIdx.x == 0) {
     ++epoch;
     if (sys_release) __threadfence_system(); else __threadfence();      // release this block's stores
@@ -139,6 +165,7 @@ __device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoc
     __threadfence();                                                     // acquire + L1 invalidate
   }
   __syncthreads();
+#endif
 }
 
 // Single-GPU barrier: every block spins on the arrive counter itself (no leader hop).
