@@ -170,7 +170,7 @@ def workload_config(args, n_dof):
     return {"workload": f"synthetic {args.grid}x{args.grid} mycelium occupancy grid per GPU (BASELINE configs[1]), "
                         f"{' and '.join(n_dof.keys())} load case(s), specimen cross-section x{args.gpus}",
             "grid": args.grid, "n_dof": n_dof, "load_cases": list(n_dof.keys()),
-            "solver": f"{args.precond if args.gpus == 1 or args.precond == 'jacobi' else 'block3'}-PCG",
+            "solver": f"{args.precond if args.gpus == 1 or args.precond == 'jacobi' or (args.precond == 'block6' and os.environ.get('MYC_DIST_BLOCK6') == '1') else 'block3'}-PCG",
             "rtol": RTOL, "grip_length": GRIP, "seed": 0,
             "l2": "operator is L2-resident at grid 512 (no flush inside a solve; see roofline_hbm for the >L2 case)",
             "parallelism": f"row-partition x{args.gpus}"}
