@@ -1,3 +1,4 @@
+# HISTORICAL: the exact command of the first round-1 GPU call of this session (K_e / assembly / fused-solve ncu captures).
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1

@@ -1,3 +1,5 @@
+# HISTORICAL: the exact command of one round-1 GPU call (results in profiles/r1_block_jacobi_groups.md).  The variant
+# libraries it names (_lb, _b6full) were A/B builds whose winners are now the defaults; see tools/next_round_ab.sh.
 # Round-1 validation of: staged assembly fill, block6/block12 preconditioners, light-barrier build.
 set -x
 mkdir -p gpurun_out

@@ -1,3 +1,5 @@
+# HISTORICAL: the exact command of one round-1 GPU call (results in profiles/r1_block_jacobi_groups.md).  The variant
+# libraries it names (_lb, _b6full) were A/B builds whose winners are now the defaults; see tools/next_round_ab.sh.
 # Final round-1 check of the shipped defaults (block6 + release/acquire barrier + staged assembly fill),
 # A/B of the full-row block6 layout, refreshed ncu launch list and fused-kernel capture.
 set -x
