@@ -32,10 +32,8 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
     ctx->no_fused_pcg = f && f[0] == '1';
     const char* g = getenv("MYC_NO_BLOCK3_SPMV");
     ctx->no_block3_spmv = g && g[0] == '1';
-    const char* b6 = getenv("MYC_DIST_BLOCK6");
-    ctx->dist_block6 = b6 && b6[0] == '1';
-    const char* ss = getenv("MYC_ASM_SHORT_SORT");
-    ctx->asm_short_sort = ss && ss[0] == '1';
+    const char* ss = getenv("MYC_ASM_FULL_SORT");
+    ctx->asm_full_sort = ss && ss[0] == '1';
     const char* d = getenv("MYC_ASM_DIRECT_FILL");
     ctx->asm_direct_fill = d && d[0] == '1';
     const char* y = getenv("MYC_NO_SYM3");
@@ -170,8 +168,14 @@ extern "C" int myc_load_case_host(myc_ctx* ctx, const double* h_coords, const in
   int32_t* d_ci = (int32_t*)b[B_CI].p;
   double* d_val = (double*)b[B_VAL].p;
   MYC_TRY(myc_assemble_numeric(ctx, d_coords, d_n1, d_n2, E, A, I, nnz, d_rp, d_ci, d_val, st));
-  const bool hint_before = ctx->csr_block3;
-  ctx->csr_block3 = true;     // what the assembler emits always has the node-block structure
+  // what the assembler emits always has the node-block structure; the caller's sticky hint is restored on
+  // every exit path (including the early error returns below)
+  struct HintGuard {
+    myc_ctx* c;
+    bool before;
+    ~HintGuard() { c->csr_block3 = before; }
+  } hint_guard{ctx, ctx->csr_block3};
+  ctx->csr_block3 = true;
   MYC_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
   MYC_TRY(myc_apply_dirichlet(ctx, n_dof, n_dof, 0, d_rp, d_ci, d_val, d_kd, d_kv, n_known, reg, d_ubc, d_rhs,
                               d_dinv, st));
@@ -194,7 +198,7 @@ extern "C" int myc_load_case_host(myc_ctx* ctx, const double* h_coords, const in
   if (h_out_iters) *h_out_iters = iters;
   if (h_out_relres) *h_out_relres = relres;
   if (h_out_nnz) *h_out_nnz = nnz;
-  if (rc != MYC_OK && rc != MYC_ERR_NOT_CONVERGED) { ctx->csr_block3 = hint_before; return rc; }
+  if (rc != MYC_OK && rc != MYC_ERR_NOT_CONVERGED) return rc;
   // U (into the rhs buffer), reactions F = K U (into the dinv buffer after the merge)
   double* d_U = d_rhs;
   MYC_TRY(myc_merge_solution(ctx, n_dof, 0, d_x, d_dinv, d_ubc, d_U, st));
@@ -211,6 +215,5 @@ extern "C" int myc_load_case_host(myc_ctx* ctx, const double* h_coords, const in
   MYC_CUDA(ctx, cudaEventElapsedTime(&ms_s, ctx->ev[3], ctx->ev[0]));
   if (h_out_ms_assemble) *h_out_ms_assemble = ms_a;
   if (h_out_ms_solve) *h_out_ms_solve = ms_s;
-  ctx->csr_block3 = hint_before;      // the caller's sticky hint is not changed by this call
   return rc;
 }

@@ -75,17 +75,21 @@ edge_emit_kernel(const int32_t* __restrict__ n1, const int32_t* __restrict__ n2,
   }
 }
 
-// Short sort (MYC_ASM_SHORT_SORT=1): the radix passes cover the source-node bits only, so a node's segment
-// arrives in emission (= element) order; this kernel orders it by destination node with a stable insertion
-// sort -- the same permutation the full-key sort produces, at O(degree^2) per node (degree <= ~6 on hyphal
-// networks; a hub of degree d costs d^2/2 moves in one thread, which is why the full sort stays the default).
+// Short sort (default; MYC_ASM_FULL_SORT=1 forces the full-key sort): the radix passes cover the source-node
+// bits only, so a node's segment arrives in emission (= element) order; this kernel orders it by destination
+// node with a stable insertion sort -- the same permutation the full-key sort produces, at O(degree^2) per
+// node (degree <= ~6 on hyphal networks).  A hub of degree d would cost d^2/2 moves in one thread, so a node
+// with more than AS_SHORT_SORT_MAX_DEG incident pairs raises *too_long and the host redoes the full sort.
+// Measured at 2048^2 (profiles/r2_ab_gpu1.md): assembly 1.93 -> 1.46 ms, CSR bit-identical.
+constexpr int AS_SHORT_SORT_MAX_DEG = 64;
 __global__ void __launch_bounds__(AS_THREADS)
 segment_order_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, const int32_t* __restrict__ edge_start,
-                     int64_t n_local, int dst_bits) {
+                     int64_t n_local, int dst_bits, int* __restrict__ too_long) {
   const uint64_t dmask = ((uint64_t)1 << dst_bits) - 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t es = edge_start[i], ee = edge_start[i + 1];
+    if (ee - es > AS_SHORT_SORT_MAX_DEG) { *too_long = 1; continue; }
     for (int32_t k = es + 1; k < ee; ++k) {
       const uint64_t kk = keys[k];
       const uint32_t vv = vals[k];
@@ -320,30 +324,40 @@ extern "C" int myc_assemble_symbolic(myc_ctx* ctx, const int32_t* d_n1, const in
     MYC_TRY(myc_ensure(ctx, ctx->sort_vals[k], (size_t)(n_edges + 1) * sizeof(uint32_t)));
   }
   int sorted = 0;
-  if (n_edges > 0) {
-    edge_emit_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, node_begin, node_end,
-                                                    dst_bits, cnt, (uint64_t*)ctx->sort_keys[0].p,
-                                                    (uint32_t*)ctx->sort_vals[0].p, deg);
+  int* too_long = bad_flag + 8;                       // zeroed with bad_flag above
+  // attempt 0: short sort (the whole pipeline runs speculatively; the hub flag is read with the nnz at the
+  // end, so the common case pays no extra host round trip); attempt 1: full-key sort
+  for (int attempt = ctx->asm_full_sort ? 1 : 0; attempt < 2; ++attempt) {
+    const bool short_sort = attempt == 0;
+    if (attempt == 1) MYC_CUDA(ctx, cudaMemsetAsync(deg, 0, (size_t)(n_local + 1) * sizeof(int32_t), st));
+    if (n_edges > 0) {
+      edge_emit_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, node_begin, node_end,
+                                                      dst_bits, cnt, (uint64_t*)ctx->sort_keys[0].p,
+                                                      (uint32_t*)ctx->sort_vals[0].p, deg);
+      MYC_LAUNCHED(ctx);
+      MYC_TRY(myc_radix_sort_pairs(ctx, n_edges, short_sort ? dst_bits : 0, key_bits, &sorted, st));
+    }
+    // per-node segments of the sorted stream
+    MYC_TRY(myc_exclusive_scan_i32(ctx, deg, deg, n_local, true, nullptr, st));
+    if (short_sort && n_edges > 0 && n_local > 0) {
+      segment_order_kernel<<<g_node, AS_THREADS, 0, st>>>((uint64_t*)ctx->sort_keys[sorted].p,
+                                                          (uint32_t*)ctx->sort_vals[sorted].p, deg, n_local, dst_bits,
+                                                          too_long);
+      MYC_LAUNCHED(ctx);
+    }
+    if (n_local > 0) {
+      block_count_kernel<<<g_node, AS_THREADS, 0, st>>>((const uint64_t*)ctx->sort_keys[sorted].p, deg,
+                                                        n_local, node_begin, dst_bits, nbc);
+      MYC_LAUNCHED(ctx);
+    }
+    MYC_TRY(myc_exclusive_scan_i32(ctx, nbc, nbc, n_local, true, d_total, st));
+    row_ptr_kernel<<<g_node, AS_THREADS, 0, st>>>(nbc, n_local, d_out_row_ptr);
     MYC_LAUNCHED(ctx);
-    MYC_TRY(myc_radix_sort_pairs(ctx, n_edges, ctx->asm_short_sort ? dst_bits : 0, key_bits, &sorted, st));
+    MYC_CUDA(ctx, cudaMemcpyAsync(h_pin, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaMemcpyAsync(h_pin + 2, too_long, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (!short_sort || !*(int*)(h_pin + 2)) break;    // no hub: the short sort's permutation stands
   }
-  // per-node segments of the sorted stream
-  MYC_TRY(myc_exclusive_scan_i32(ctx, deg, deg, n_local, true, nullptr, st));
-  if (ctx->asm_short_sort && n_edges > 0 && n_local > 0) {
-    segment_order_kernel<<<g_node, AS_THREADS, 0, st>>>((uint64_t*)ctx->sort_keys[sorted].p,
-                                                        (uint32_t*)ctx->sort_vals[sorted].p, deg, n_local, dst_bits);
-    MYC_LAUNCHED(ctx);
-  }
-  if (n_local > 0) {
-    block_count_kernel<<<g_node, AS_THREADS, 0, st>>>((const uint64_t*)ctx->sort_keys[sorted].p, deg,
-                                                      n_local, node_begin, dst_bits, nbc);
-    MYC_LAUNCHED(ctx);
-  }
-  MYC_TRY(myc_exclusive_scan_i32(ctx, nbc, nbc, n_local, true, d_total, st));
-  row_ptr_kernel<<<g_node, AS_THREADS, 0, st>>>(nbc, n_local, d_out_row_ptr);
-  MYC_LAUNCHED(ctx);
-  MYC_CUDA(ctx, cudaMemcpyAsync(h_pin, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  MYC_CUDA(ctx, cudaStreamSynchronize(st));
   const int64_t nnz = 9 * h_pin[0];
   if (nnz >= ((int64_t)1 << 31)) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "assemble_symbolic: nnz %lld exceeds int32 row_ptr", (long long)nnz);
   *h_out_nnz = nnz;

@@ -9,6 +9,7 @@
 
 #define MYC_SM_COUNT_FALLBACK 148
 #define MYC_MAX_WORLD 8          // ranks the NVLink peer-memory PCG supports (one HGX board)
+#define MYC_MAXIT_LIMIT 4000000  // PCG iterations one solve may run (32-bit barrier epochs of the persistent kernels)
 
 // Growable device scratch buffer owned by the context.
 struct DevBuf {
@@ -32,8 +33,8 @@ struct myc_ctx {
   bool no_block3_spmv = false;     // MYC_NO_BLOCK3_SPMV=1: ignore the node-block hint
   bool no_sym3 = false;            // MYC_NO_SYM3=1: the fused PCG streams the CSR, not the symmetric block view
   bool no_halo_overlap = true;     // MYC_HALO_OVERLAP=1 enables the gated sweep (halo waits inside the sweep)
-  bool dist_block6 = false;        // MYC_DIST_BLOCK6=1: 6x6 Jacobi blocks in the multi-GPU solver kernel (caller aligns the cuts)
-  bool asm_short_sort = false;     // MYC_ASM_SHORT_SORT=1: radix passes over the source-node bits only + per-node neighbour ordering
+  bool asm_full_sort = false;      // MYC_ASM_FULL_SORT=1: radix passes over the whole (source, destination) key instead of the
+                                   // source bits + per-node neighbour ordering (the default since round 2)
   bool asm_direct_fill = false;    // MYC_ASM_DIRECT_FILL=1: numeric assembly stores rows straight to global memory (no staging)
   bool csr_block3 = false;         // caller's hint: the CSR it passes has the 3x3 node-block structure
 
@@ -61,6 +62,11 @@ struct myc_ctx {
   double prof_ms = 0.0, prof_bytes = 0.0;
   int64_t prof_samples = 0, prof_launches = 0;
   int prof_op = 0;               // operator the last profiled fused solve streamed (0/1 CSR, 2 sym3)
+
+  // ---- per-DEVICE one-time kernel setup (cudaFuncSetAttribute is per device; a process may hold one
+  // context per GPU, so these flags live here and not in function-local statics)
+  int fused_max_blocks_per_sm = -1;       // pcg_fused.cu: opt-in shared memory set + occupancy queried
+  int amg_max_blocks_per_sm = -1;         // pcg_amg.cu
 
   // ---- assembly plan retained between symbolic and numeric
   bool plan_valid = false;

@@ -273,6 +273,10 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       (precond != MYC_PC_JACOBI && !block3 && !group) || (block3 && (!d_binv || n_rows % 3)) ||
       (group && n_rows > 0 && !d_binv))
     MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "pcg_solve: bad argument");
+  // the persistent kernel's barrier epochs are 32-bit counters of (barriers x blocks): 2 barriers per
+  // iteration x 148 blocks wrap after ~14.5 M iterations
+  if (maxit > MYC_MAXIT_LIMIT)
+    MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "pcg_solve: maxit %lld exceeds the supported %lld", (long long)maxit, (long long)MYC_MAXIT_LIMIT);
   MYC_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   MYC_TRY(prepare_solver_buffers(ctx, n_rows, n_cols_global, block3));
@@ -335,7 +339,7 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       }
       if (h_out_iters) *h_out_iters = (int64_t)fin.iters;
       if (h_out_relres) *h_out_relres = rel;
-      if (fin.breakdown || !(rel == rel))
+      if (fin.breakdown || !(rel == rel) || !isfinite(fin.rr_final))
         MYC_FAIL(ctx, MYC_ERR_BREAKDOWN, "pcg_solve (fused): breakdown after %lld iterations, r.r = %g",
                  (long long)fin.iters, fin.rr_final);
       if (!fin.done)

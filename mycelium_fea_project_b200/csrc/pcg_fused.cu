@@ -115,32 +115,6 @@ __device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoc
                                               F&& leader_work) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
-#ifdef MYC_LIGHT_DIST_BARRIER
-  // A/B build (not measured yet): the same release/acquire chain with the redundant fences removed, as in
-  // local_barrier.  arrive = acq_rel atomic (releases this block's stores, and lets the last arriver acquire
-  // everybody's); blocks that stored into a peer GPU still issue the system-scope fence first; the leader
-  // publishes with st.release, the others wake on ld.acquire (whose CCTL.IVALL invalidates L1).
-  if (threadIdx.x == 0) {
-    ++epoch;
-    if (sys_release) __threadfence_system();
-    unsigned old;
-    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(&a.bar[0]), "r"(1u) : "memory");
-    *s_leader = (old == epoch * gridDim.x - 1u);
-  }
-  __syncthreads();
-  if (*s_leader && warp == 0) {
-    __syncwarp();
-    leader_work(lane);
-    __syncwarp();
-    if (lane == 0) st_release_gpu(&a.bar[1], epoch);
-  }
-  if (threadIdx.x == 0) {
-    unsigned spins = 0;
-    while (ld_acquire_gpu(&a.bar[1]) < epoch)
-      if (++spins > FU_SPIN_LIMIT) __trap();
-  }
-  __syncthreads();
-#else
   if (threadIdx.x == 0) {
     ++epoch;
     if (sys_release) __threadfence_system(); else __threadfence();      // release this block's stores
@@ -165,7 +139,6 @@ __device__ __forceinline__ void fused_barrier(const FusedArgs& a, unsigned& epoc
     __threadfence();                                                     // acquire + L1 invalidate
   }
   __syncthreads();
-#endif
 }
 
 // Single-GPU barrier: every block spins on the arrive counter itself (no leader hop).
@@ -261,14 +234,11 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
   else tm_pipe_init(pp, fu_smem, FU_WARPS, warp, lane, Cfg::CAP);
   const int32_t nnz_total = a.rp[n];
   // Global warp number: tiles (and the vector pass's row chunks) are dealt round-robin over it.  Block-major
-  // numbering gives the last, partial round to the first blocks only: at 512^2, 17,474 tiles over 4,736 warps
-  // = 4 tiles per warp in blocks 0..101 and 3 in blocks 103..147.  -DMYC_BLOCK_FASTEST_WARPS numbers the warps
-  // block-fastest so that every SM gets the same share of the partial round (A/B build, not measured yet).
-#ifdef MYC_BLOCK_FASTEST_WARPS
+  // numbering would give the last, partial round to the first blocks only (at 512^2: 17,474 tiles over 4,736
+  // warps = 4 tiles per warp in blocks 0..101 and 3 in blocks 103..147); numbering the warps block-fastest
+  // gives every SM the same share of the partial round: 157.1 -> 153.8 ms per 512^2 solve, same iteration
+  // counts, whole GPU suite green (profiles/r2_ab_gpu1.md).
   const int64_t gw = (int64_t)warp * gridDim.x + blockIdx.x;
-#else
-  const int64_t gw = (int64_t)blockIdx.x * FU_WARPS + warp;
-#endif
   const int64_t n_warps = (int64_t)gridDim.x * FU_WARPS;
 
   // store one entry of u locally and into every GPU that gathers it
@@ -482,6 +452,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) pcg_fused_kernel(FusedArgs a) {
     FT_MARK(1);
     const double gamma = s_tot[0], delta = s_tot[1];
     rr = s_tot[2];
+    if (!isfinite(rr)) { status = 2; break; }            // NaN / inf in K, b or x0: breakdown, not convergence
     if (!(rr > tol2)) { status = 1; break; }             // converged (x, r are consistent)
     if (it >= a.maxit) { status = 0; break; }
     const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
@@ -626,7 +597,7 @@ template <int PC, int OP, bool DIST>
 const void* fused_fn() { return (const void*)pcg_fused_kernel<PC, OP, DIST>; }
 constexpr int FU_VARIANTS = 21;
 // index = dist*6 + op*2 + pc for pc 0 / 1;  12 + op*2 + (pc - 2) for the single-GPU node-group blocks;
-// 18 + op for the 6x6 blocks on several GPUs (rank boundaries on even nodes, MYC_DIST_BLOCK6=1)
+// 18 + op for the 6x6 blocks on several GPUs (needs rank boundaries on even nodes: dist.py cuts there)
 const void* fused_variant(int idx) {
   static const void* tab[FU_VARIANTS] = {
       fused_fn<0, 0, false>(), fused_fn<1, 0, false>(), fused_fn<0, 1, false>(), fused_fn<1, 1, false>(),
@@ -650,14 +621,13 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
   *handled = 0;
   if (ctx->no_fused_pcg) return MYC_OK;
   const bool dist = ctx->world > 1;
-  // node-group blocks: rows of a block must be rank-local; on several GPUs only the 6x6 blocks, opt-in
-  if (pc >= 2 && (row_offset % (pc == 2 ? 6 : 12) != 0 || ((uintptr_t)d_binv & 15u) != 0 ||
-                  (dist && (pc != 2 || !ctx->dist_block6))))
+  // node-group blocks: rows of a block must be rank-local; on several GPUs only the 6x6 blocks
+  if (pc >= 2 && (row_offset % (pc == 2 ? 6 : 12) != 0 || ((uintptr_t)d_binv & 15u) != 0 || (dist && pc != 2)))
     return MYC_OK;
   if (dist && (!ctx->peer_ok || ctx->peer_cap < n_cols_global || ctx->world > MYC_MAX_WORLD)) return MYC_OK;
   if (!dist && n_rows == 0) return MYC_OK;
   if ((((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0) return MYC_OK;   // (same allocator on every rank)
-  static int max_blocks_per_sm = -1;
+  int& max_blocks_per_sm = ctx->fused_max_blocks_per_sm;      // per device (the attribute below is per device)
   if (max_blocks_per_sm < 0) {
     int mn = 1 << 30;
     for (int k = 0; k < FU_VARIANTS; ++k) {

@@ -356,12 +356,9 @@ template <class Cfg, class Epi>
 static inline int myc_launch_spmv_tma(myc_ctx* ctx, int64_t n_rows, const int32_t* rp, const int32_t* ci,
                                       const double* v, const double* x, const Epi& epi, double* partials,
                                       unsigned* counter, double* out, const int* done, cudaStream_t st) {
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
-    MYC_CUDA(ctx, cudaFuncSetAttribute(myc_spmv_tma_kernel<Cfg, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tm_smem_bytes(TM_WARPS, Cfg::CAP)));
-    attr_set = true;
-  }
+  // the opt-in is per device and costs ~1 us: set it on every launch (a process may drive several GPUs)
+  MYC_CUDA(ctx, cudaFuncSetAttribute(myc_spmv_tma_kernel<Cfg, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tm_smem_bytes(TM_WARPS, Cfg::CAP)));
   const int64_t n_tiles = ceil_div64(n_rows, Cfg::ROWS);
   const int grid = grid_for(ctx, ceil_div64(n_tiles, TM_WARPS), TM_BLOCKS_PER_SM);
   myc_spmv_tma_kernel<Cfg, Epi><<<grid, TM_THREADS, tm_smem_bytes(TM_WARPS, Cfg::CAP), st>>>(n_rows, rp, ci, v, x, epi, partials, counter,

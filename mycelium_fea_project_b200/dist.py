@@ -151,12 +151,9 @@ class DistributedSolver:
             dist.all_gather_object(out, arr)
             return out
 
-        # MYC_DIST_BLOCK6=1 (opt-in, not yet measured on N > 1 GPUs): cuts on even nodes so that the 6x6
-        # Jacobi blocks stay rank-local and "block6" can run in the multi-GPU solver kernel too
-        import os
-        self.block6 = os.environ.get("MYC_DIST_BLOCK6") == "1"
-        self.plan = make_plan(n1, n2, active, self.n_nodes, self.rank, self.world, all_gather,
-                              align=2 if self.block6 else 1)
+        # cuts on even nodes, so that the aligned 6x6 Jacobi blocks stay rank-local ("block6" on N > 1 GPUs)
+        self.block6 = True
+        self.plan = make_plan(n1, n2, active, self.n_nodes, self.rank, self.world, all_gather, align=2)
         self.mesh = dv.DeviceMesh.from_host(coords, n1, n2, active, device=self.ctx.device)
         if self.world > 1 and self.ctx.world == 1:
             path = nccl_library_path().encode()
@@ -239,8 +236,8 @@ class DistributedSolver:
         td = lambda a, dt: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
         kd, kv = td(known_dofs, np.int64), td(known_vals, np.float64)
         if precond == "block12" or (precond == "block6" and not (self.block6 and K.row_offset % 6 == 0)):
-            # the node-group blocks need rank boundaries aligned to the groups: without MYC_DIST_BLOCK6=1
-            # a row-partitioned solve uses the 3x3 node blocks
+            # the 12-row groups would need cuts on multiples of 4 nodes: a row-partitioned solve uses the
+            # 3x3 node blocks instead
             precond = "block3"
         sysd = dv.apply_dirichlet(ctx, K, kd, kv, reg, precond=precond)
         self._ensure_peer(K.n_cols)

@@ -44,7 +44,7 @@ def test_partition_and_plan_single_process():
 
 
 def test_aligned_partition_keeps_node_pairs_on_one_rank():
-    """MYC_DIST_BLOCK6 layout: every interior cut on an even node (or at the end), still balanced."""
+    """The multi-GPU partition (cuts aligned to the 6x6 Jacobi blocks): every interior cut on an even node (or at the end), still balanced."""
     for n, world in [(10, 3), (11, 4), (174738, 8), (7, 8), (2, 4), (0, 2), (1067, 2), (1, 1)]:
         off = md.partition_nodes(n, world, align=2)
         assert off[0] == 0 and off[-1] == n and np.all(np.diff(off) >= 0)

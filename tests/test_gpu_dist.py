@@ -21,12 +21,10 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, N, precond, ret, no_peer=False, shape=None, case="Y", dist_block6=False):
+def _worker(rank, world, port, N, precond, ret, no_peer=False, shape=None, case="Y"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     if no_peer:
         os.environ["MYC_NO_PEER"] = "1"
-    if dist_block6:
-        os.environ["MYC_DIST_BLOCK6"] = "1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -68,7 +66,7 @@ def _worker(rank, world, port, N, precond, ret, no_peer=False, shape=None, case=
 
 @pytest.mark.parametrize("precond,no_peer", [("jacobi", False), ("jacobi", True), ("block3", False)])
 def test_two_gpu_solve_matches_oracle(precond, no_peer):
-    """jacobi/False: fused persistent kernel over NVLink peer memory; jacobi/True and block3: NCCL loop."""
+    """no_peer False: fused persistent kernel over NVLink peer memory (jacobi and block3); True: NCCL loop."""
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
@@ -80,16 +78,13 @@ def test_two_gpu_solve_matches_oracle(precond, no_peer):
         assert ret[0][3] and ret[1][3], "peer-memory path was not enabled on this box"
 
 
-@pytest.mark.skipif(os.environ.get("MYC_TEST_DIST_BLOCK6") != "1",
-                    reason="opt-in: 6x6 Jacobi blocks in the multi-GPU solver kernel (MYC_DIST_BLOCK6=1) have not been "
-                           "run on N > 1 GPUs yet; set MYC_TEST_DIST_BLOCK6=1 to exercise them")
-def test_two_gpu_block6_opt_in():
+def test_two_gpu_block6():
     """Cuts on even nodes, block6 inside the peer-memory solver kernel: same parity bars, and fewer
     iterations than the 3x3 node blocks need on the same two-rank problem."""
     world = 2
     mgr = mp.Manager()
     ret6, ret3 = mgr.dict(), mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), 96, "block6", ret6, False, None, "Y", True), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 96, "block6", ret6, False), nprocs=world, join=True)
     mp.spawn(_worker, args=(world, _free_port(), 96, "block3", ret3, False), nprocs=world, join=True)
     assert len(ret6) == world and ret6[0][0] == ret6[1][0] and ret6[0][2] == ret6[1][2]
     assert ret6[0][0] < ret3[0][0], (ret6[0][0], ret3[0][0])

@@ -189,20 +189,34 @@ def test_assembly_staged_fill_matches_direct_fill(monkeypatch):
         ctx2.close()
 
 
-@pytest.mark.skipif(os.environ.get("MYC_TEST_SHORT_SORT") != "1",
-                    reason="opt-in: MYC_ASM_SHORT_SORT=1 (radix passes over the source bits only) has not run on a GPU yet")
-def test_assembly_short_sort_opt_in(monkeypatch):
-    """Same CSR, bit for bit, as the full-key sort (logic checked on the CPU in test_kernel_logic_host.py)."""
+def test_assembly_short_and_full_sort_agree(monkeypatch):
+    """The default short sort (radix passes over the source bits + per-node neighbour ordering) gives the same
+    CSR, bit for bit, as the full-key sort (MYC_ASM_FULL_SORT=1); logic also checked on the CPU in
+    test_kernel_logic_host.py."""
     coords, n1, n2 = synth_network(128, seed=7)
     act = np.random.default_rng(7).random(len(n1)) > 0.2
     ref = fs.assemble_global_stiffness(coords, (n1, n2), act)
-    monkeypatch.setenv("MYC_ASM_SHORT_SORT", "1")
+    monkeypatch.setenv("MYC_ASM_FULL_SORT", "1")
     ctx2 = dv.Context(0)
     try:
         K = dv.assemble(ctx2, dv.DeviceMesh.from_host(coords, n1, n2, act), fs.E_mod, fs.A, fs.I).to_scipy()
     finally:
         ctx2.close()
     assert np.array_equal(K.indptr, ref.indptr) and np.array_equal(K.indices, ref.indices) and np.array_equal(K.data, ref.data)
+
+
+def test_assembly_hub_node_falls_back_to_full_sort(ctx):
+    """A node with more incident elements than the short sort orders in one thread (64) makes the assembler
+    redo the symbolic phase with the full-key sort: same CSR as the oracle."""
+    rng = np.random.default_rng(3)
+    n = 200
+    coords = np.c_[rng.random((n, 2)), np.zeros(n)]
+    n1 = np.zeros(n - 1, dtype=np.int32)                 # star: node 0 is a hub of degree 199
+    n2 = np.arange(1, n, dtype=np.int32)
+    n1 = np.concatenate([n1, np.arange(1, n - 1, dtype=np.int32)])
+    n2 = np.concatenate([n2, np.arange(2, n, dtype=np.int32)])
+    K = dv.assemble(ctx, dv.DeviceMesh.from_host(coords, n1, n2), fs.E_mod, fs.A, fs.I).to_scipy()
+    _assert_csr_parity(K, fo.assemble_global_stiffness(coords, n1, n2, np.ones(len(n1), bool)))
 
 
 def test_assembly_row_block_is_slice_of_global(ctx):
