@@ -51,7 +51,9 @@ enum {
   MYC_PC_JACOBI = 0,   /* point Jacobi                                                          */
   MYC_PC_BLOCK3 = 1,   /* 3x3 node blocks                                                       */
   MYC_PC_BLOCK6 = 2,   /* aligned blocks of 2 consecutive nodes (rows 6k .. 6k+5)               */
-  MYC_PC_BLOCK12 = 3   /* aligned blocks of 4 consecutive nodes (rows 12k .. 12k+11)            */
+  MYC_PC_BLOCK12 = 3,  /* aligned blocks of 4 consecutive nodes (rows 12k .. 12k+11)            */
+  MYC_PC_AMG = 4       /* aggregation-multigrid V-cycle (myc_amg_setup): the counterpart of the
+                          reference's "gamg" entry, src/fea_petsc_solverAndPC.cpp:331              */
 };
 
 int myc_abi_version(void);
@@ -152,6 +154,22 @@ int64_t myc_block_inverse_size(int nodes_per_block, int64_t n_rows);
 int myc_block_inverse_packed(myc_ctx* ctx, int nodes_per_block, int64_t n_rows, int64_t row_offset,
                              const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
                              const double* d_dinv, double reg, double* d_out_pinv, void* stream);
+
+/* Aggregation multigrid for MYC_PC_AMG (the multigrid row of the reference's PETSc preconditioner menu,
+ * src/fea_petsc_solverAndPC.cpp:330-331, restated for this operator; algorithm in oracle/amg_oracle.py).
+ * Builds, inside the context, a hierarchy of Galerkin operators on node aggregates (pairwise matching by
+ * coupling strength + joining of leftovers; piecewise-constant prolongation per displacement component;
+ * 3x3-block Jacobi smoothing) for the operator A of myc_apply_dirichlet: call it after myc_apply_dirichlet
+ * with the same CSR and the d_dinv it produced, then pass MYC_PC_AMG (d_binv = NULL) to myc_pcg_solve with
+ * the same d_row_ptr / d_dinv.  The hierarchy stays valid for further right-hand sides on the same operator
+ * and Dirichlet set.  *h_out_levels = 0 means "not applicable" (the CSR lacks the 3x3 node-block structure or
+ * blockwise symmetry, or a node has only some of its DOFs prescribed): use a Jacobi-type preconditioner.
+ * myc_amg_level_info: out[0] nodes, out[1] blocks of `level`, out[2] number of levels, out[3] setup time (us);
+ * d_out_agg (may be NULL): the level's node -> aggregate map (int32, -1 = not represented on the next level). */
+int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
+                  const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
+                  const double* d_dinv, double reg, int* h_out_levels, void* stream);
+int myc_amg_level_info(myc_ctx* ctx, int level, int64_t* h_out4, int32_t* d_out_agg, void* stream);
 
 /* Structure parity aid: the explicit reduced matrix K[free][:,free] the reference builds
  * (src/fea_solver.py:118), as CSR over the compacted free numbering.  Two-phase like assembly:

@@ -24,7 +24,9 @@ MYC_PC_JACOBI = 0
 MYC_PC_BLOCK3 = 1
 MYC_PC_BLOCK6 = 2
 MYC_PC_BLOCK12 = 3
-PRECONDITIONERS = {"jacobi": MYC_PC_JACOBI, "block3": MYC_PC_BLOCK3, "block6": MYC_PC_BLOCK6, "block12": MYC_PC_BLOCK12}
+MYC_PC_AMG = 4
+PRECONDITIONERS = {"jacobi": MYC_PC_JACOBI, "block3": MYC_PC_BLOCK3, "block6": MYC_PC_BLOCK6, "block12": MYC_PC_BLOCK12,
+                   "amg": MYC_PC_AMG}
 
 _ERR_NAMES = {-1: "BAD_ARG", -2: "CUDA", -3: "NCCL", -4: "NOT_CONVERGED", -5: "BREAKDOWN",
               -6: "CAPACITY", -7: "STATE"}
@@ -72,6 +74,8 @@ SIGNATURES = {
     "myc_block3_inverse": [_p, _i64, _i64, _p, _p, _p, _p, _f64, _p, _p],
     "myc_block_inverse_size": [_int, _i64],
     "myc_block_inverse_packed": [_p, _int, _i64, _i64, _p, _p, _p, _p, _f64, _p, _p],
+    "myc_amg_setup": [_p, _i64, _i64, _i64, _p, _p, _p, _p, _f64, C.POINTER(C.c_int), _p],
+    "myc_amg_level_info": [_p, _int, _pi64, _p, _p],
     "myc_reduce_csr": [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _pi64, _pi64, _p],
     "myc_spmv": [_p, _i64, _p, _p, _p, _p, _p, _p],
     "myc_pcg_solve": [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _int, _f64, _f64, _f64, _i64, _p,

@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 int myc_dist_destroy(myc_ctx* ctx);   // dist.cu
+int myc_amg_destroy(myc_ctx* ctx);    // amg_setup.cu
 
 static char g_create_err[256] = "no error";
 
@@ -55,7 +56,7 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
   }
   if (e == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_pinned, 4096, cudaHostAllocDefault);
-  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
   if (e != cudaSuccess) {
     snprintf(g_create_err, sizeof(g_create_err), "context setup failed: %s", cudaGetErrorString(e));
     delete ctx;
@@ -70,6 +71,7 @@ extern "C" int myc_destroy(myc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   myc_dist_destroy(ctx);
+  myc_amg_destroy(ctx);
   DevBuf* all[] = {&ctx->scan_tmp, &ctx->sort_keys[0], &ctx->sort_keys[1], &ctx->sort_vals[0], &ctx->sort_vals[1],
                    &ctx->sort_table, &ctx->edge_cnt, &ctx->node_deg, &ctx->node_bc, &ctx->partials, &ctx->scalars,
                    &ctx->vec[0], &ctx->vec[1], &ctx->vec[2], &ctx->vec[3], &ctx->vec[4], &ctx->vec[5], &ctx->misc,
@@ -77,7 +79,7 @@ extern "C" int myc_destroy(myc_ctx* ctx) {
   for (DevBuf* b : all) if (b->p) cudaFree(b->p);
   for (DevBuf& b : ctx->lc) if (b.p) cudaFree(b.p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (cudaEvent_t e : ctx->prof_ev) if (e) cudaEventDestroy(e);
   delete ctx;
   return MYC_OK;

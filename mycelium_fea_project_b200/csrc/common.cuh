@@ -17,7 +17,8 @@ struct DevBuf {
   size_t cap = 0;
 };
 
-struct NcclApi;  // dist.cu
+struct NcclApi;   // dist.cu
+struct AmgState;  // amg.cuh
 
 struct PeerRange {  // half-open DOF range [lo, hi) of a global-length vector
   int64_t lo = 0, hi = 0;
@@ -51,9 +52,11 @@ struct myc_ctx {
   DevBuf vec[6];                // PCG work vectors (r, p(global), Ap, ...)
   DevBuf misc;                  // small temporaries (flags, gather-sum output ...)
   DevBuf lc[14];                // device copies owned by myc_load_case_host
-  DevBuf sym_val, sym_col;      // symmetric 3x3 block view of K for the fused PCG (spmv_sym3.cuh)
+  DevBuf sym_val, sym_col;      // symmetric 3x3 block view of K for the persistent solver kernels (spmv_sym3.cuh)
+  int sym_owner = 0;            // 1: sym_val / sym_col are level 0 of the multigrid hierarchy below
+  AmgState* amg = nullptr;      // aggregation-multigrid hierarchy of the last myc_amg_setup (amg.cuh)
   void* h_pinned = nullptr;     // 4 KB pinned staging for host scalars
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [4], [5]: multigrid setup timing
 
   // ---- sampled per-launch timing of the fused SpMV (bench.py roofline; off by default)
   static constexpr int PROF_PAIRS = 128;
@@ -89,6 +92,7 @@ struct myc_ctx {
   int64_t peer_cap = 0;              // capacity of the u vector in doubles
   bool peer_ok = false;
   unsigned peer_epoch_red = 0, peer_epoch_halo = 0;
+  unsigned amg_epoch_red = 0, amg_epoch_halo = 0;     // the same for the multigrid solver kernel's own flag block
 };
 
 #define MYC_FAIL(ctx, code, ...)                                   \

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "spmv.cuh"
 #include "spmv_tma.cuh"
+#include "amg.cuh"
 
 int myc_dist_allreduce_dev(myc_ctx* ctx, double* d_buf, int n, cudaStream_t st);   // dist.cu
 int myc_dist_halo(myc_ctx* ctx, double* d_x_global, cudaStream_t st);              // dist.cu
@@ -268,9 +269,10 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   if (n_rows == 0 && (precond == MYC_PC_BLOCK6 || precond == MYC_PC_BLOCK12)) precond = MYC_PC_JACOBI;   // nothing to solve
   const bool block3 = precond == MYC_PC_BLOCK3;
   const bool group = precond == MYC_PC_BLOCK6 || precond == MYC_PC_BLOCK12;     // fused single-GPU kernel only
+  const bool amg = precond == MYC_PC_AMG;                                       // hierarchy from myc_amg_setup
   if (n_rows < 0 || n_cols_global < n_rows || row_offset < 0 || row_offset + n_rows > n_cols_global ||
       !d_row_ptr || (n_rows > 0 && (!d_rhs || !d_dinv || !d_x)) || maxit < 0 ||
-      (precond != MYC_PC_JACOBI && !block3 && !group) || (block3 && (!d_binv || n_rows % 3)) ||
+      (precond != MYC_PC_JACOBI && !block3 && !group && !amg) || (block3 && (!d_binv || n_rows % 3)) ||
       (group && n_rows > 0 && !d_binv))
     MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "pcg_solve: bad argument");
   // the persistent kernel's barrier epochs are 32-bit counters of (barriers x blocks): 2 barriers per
@@ -305,16 +307,25 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   {
     int handled = 0, op_used = 0;
     if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
-    MYC_TRY(myc_pcg_fused_try(ctx, n_rows, n_cols_global, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv,
-                              (block3 || group) ? d_binv : nullptr, precond, reg, maxit, d_x, st, &handled, &op_used));
+    if (amg) {
+      op_used = 2;
+      MYC_TRY(myc_pcg_amg_try(ctx, n_rows, n_cols_global, row_offset, d_row_ptr, d_dinv, reg, maxit, d_x, st, &handled));
+    } else {
+      MYC_TRY(myc_pcg_fused_try(ctx, n_rows, n_cols_global, row_offset, d_row_ptr, d_col_idx, d_val, d_dinv,
+                                (block3 || group) ? d_binv : nullptr, precond, reg, maxit, d_x, st, &handled, &op_used));
+    }
     if (handled) {
       if (ctx->prof_on) MYC_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
       MYC_CUDA(ctx, cudaMemcpyAsync(h_sc, sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
       MYC_CUDA(ctx, cudaStreamSynchronize(st));
       const PcgScalars fin = *h_sc;
-      if (dist) {
+      if (dist && !amg) {
         ctx->peer_epoch_red = (unsigned)fin.pAp;
         ctx->peer_epoch_halo = (unsigned)fin.rz_old;
+      }
+      if (dist && amg) {
+        ctx->amg_epoch_red = (unsigned)fin.pAp;
+        ctx->amg_epoch_halo = (unsigned)fin.rz_old;
       }
       if (getenv("MYC_FUSED_TIMING_PRINT"))
         fprintf(stderr, "[fused] block0 ns/iter: sweep %.0f  barrier+reduce %.0f  vector %.0f  barrier %.0f  (iters %lld)\n",
@@ -330,7 +341,8 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
         ctx->prof_launches += 1;
         // bytes the sweep streams per iteration: CSR 12 B/nnz, symmetric block view 52 B per 9 nnz
         const double mat = op_used == 2 ? (52.0 / 9.0) * h_nnz : 12.0 * h_nnz;
-        ctx->prof_bytes += ((double)fin.iters + 1.0) * (mat + 20.0 * (double)n_rows) +
+        if (amg) ctx->prof_bytes += ((double)fin.iters + 1.0) * myc_amg_bytes_per_iteration(ctx);
+        else ctx->prof_bytes += ((double)fin.iters + 1.0) * (mat + 20.0 * (double)n_rows) +
                            (double)fin.iters * (double)n_rows *           // + the inverse blocks of the preconditioner
                                // algorithmic minimum: the symmetric inverse, R(R+1)/2 doubles per R rows
                                // (the 6x6 blocks are STORED row by row, 48 B per row; not counted)
@@ -348,6 +360,7 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       return MYC_OK;
     }
   }
+  if (amg) MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve(MYC_PC_AMG): the persistent multigrid solver kernel is unavailable here");
   if (group)
     MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve: MYC_PC_BLOCK6 / MYC_PC_BLOCK12 run only in the single-GPU persistent solver "
                                  "kernel, which is unavailable here (multi-GPU context, MYC_NO_FUSED_PCG, unaligned arrays "

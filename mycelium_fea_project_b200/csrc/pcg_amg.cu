@@ -1,0 +1,544 @@
+// K5 with the multigrid preconditioner: the whole AMG-preconditioned CG solve is ONE persistent cooperative
+// launch per GPU (one 1024-thread block per SM), like pcg_fused.cu, with the V-cycle inside the iteration loop.
+//
+// Per iteration (single-reduction CG of Chronopoulos & Gear; u = M^-1 r is the V-cycle of amg.cuh):
+//   D0   p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s        (all CG recurrences, one pass)
+//        fused with the pre-smoothing of level 0 from a zero guess: e_0 = omega D_0^-1 r
+//   down for l = 0 .. L-2:   R_l: t_l = r_l - A_l e_l        (TMA-pipelined sweep over the level's block view)
+//                            D_l+1: r_l+1 = P^T t_l (each coarse row gathers its members: no atomics),
+//                                   e_l+1 = omega D^-1 r_l+1
+//   coarsest: AMG_COARSE_SWEEPS - 1 further sweeps  e += omega D^-1 (r - A e)
+//   up   for l = L-2 .. 0:   U1_l: e_l += AMG_SCALE * P e_l+1;   U2_l: e_l += omega D^-1 (r_l - A_l e_l)  (sweep)
+//   CG   w = A_0 u + reg u with gamma = r.u, delta = w.u, r.r folded into the sweep's epilogue -> reduction
+// Every phase ends in a grid barrier.  Phases whose output another GPU gathers (the e vectors read by a sweep)
+// also store the rows a neighbour needs straight into that neighbour's arena (P2P over NVLink) and end in a
+// halo barrier (neighbour flags); restriction and prolongation are rank-local because aggregates never span
+// ranks.  Vector passes deal rows in chunks of 30 per warp (10 whole nodes), the lane of row (node, c) gets its
+// siblings' values by shuffle and applies row c of the symmetric 3x3 inverse -- the same row-per-lane layout as
+// the sweep's epilogue, so all accesses are coalesced.
+#include "amg.cuh"
+#include "spmv_sym3.cuh"
+
+namespace {
+
+constexpr int AG_WARPS = 32;
+constexpr int AG_THREADS = 32 * AG_WARPS;
+constexpr unsigned AG_SPIN_LIMIT = 1u << 28;
+static_assert(AMG_COARSE_SWEEPS >= 2 && AMG_COARSE_SWEEPS % 2 == 0, "the coarsest level's result must land in buffer 1");
+
+struct AgPeerSync {                       // lives behind the vector arena in each rank's IPC-shared buffer
+  double sums[2][MYC_MAX_WORLD][4];       // [parity][writer rank][gamma, delta, r.r, -]
+  unsigned flag_red[MYC_MAX_WORLD];       // written by rank q: reductions q has published
+  unsigned flag_halo[MYC_MAX_WORLD];      // written by rank q: halo phases q has completed
+};
+
+struct AmgArgs {
+  const AmgLevelDev* lv;
+  int n_levels;
+  double* arena[MYC_MAX_WORLD];           // vector arena of every rank ([rank] = own)
+  AgPeerSync* sync[MYC_MAX_WORLD];
+  const double* mask0;                    // level-0 Jacobi diagonal: 0 marks a known row
+  double* x;
+  double* w;
+  double* p;
+  double* s;
+  double reg;
+  long long maxit;
+  double* partials;                       // [gridDim][3]
+  unsigned* bar;                          // [0] arrive counter, [1] release epoch
+  double* gsum;                           // [2][4]
+  PcgScalars* sc;
+  int world, rank;
+  unsigned epoch_red0, epoch_halo0;
+  unsigned recv_mask_all;                 // peers this rank gathers from on any level
+};
+
+__device__ __forceinline__ unsigned ag_ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ag_ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ag_st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ag_ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid barrier of one GPU: every block arrives with one release-atomic and spins on the counter with an
+// acquire load (whose CCTL.IVALL invalidates the SM's L1) -- see local_barrier in pcg_fused.cu.
+__device__ __forceinline__ void ag_grid_barrier(unsigned* bar, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++epoch;
+    const unsigned target = epoch * gridDim.x;
+    unsigned spins = 0;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+    while (ag_ld_acquire_gpu(bar) < target)
+      if (++spins > AG_SPIN_LIMIT) __trap();
+  }
+  __syncthreads();
+}
+
+// z = (D^-1 v)_row for the row-per-lane layout: lanes 3q, 3q+1, 3q+2 (< 30) hold the rows of one node.
+// All 32 lanes call; `ok` lanes get their row of the symmetric inverse (xx xy xz yy yz zz) applied.
+__device__ __forceinline__ double ag_dinv_apply(const double* __restrict__ dinv, int64_t row, bool ok, double v, int lane) {
+  const int c = lane % 3;
+  const int src = lane < 30 ? lane - c : 0;
+  const double v0 = __shfl_sync(0xffffffffu, v, src);
+  const double v1 = __shfl_sync(0xffffffffu, v, src + 1);
+  const double v2 = __shfl_sync(0xffffffffu, v, src + 2);
+  if (!ok) return 0.0;
+  const double* d = dinv + 6 * (row / 3);
+  // row c of [[d0 d1 d2] [d1 d3 d4] [d2 d4 d5]]
+  const double m0 = d[c], m1 = d[c == 0 ? 1 : c + 2], m2 = d[c + 2 + (c > 0)];
+  return m0 * v0 + m1 * v1 + m2 * v2;
+}
+
+// stores one row of a gathered correction vector: own arena, plus every peer that gathers that row
+template <bool DIST>
+struct AgPut {
+  const AmgArgs* a;
+  __device__ __forceinline__ bool operator()(const AmgLevelDev& L, int k, int64_t row, double val) const {
+    const int64_t g = 3 * (int64_t)L.node_off + row;
+    a->arena[a->rank][L.e_off[k] + g] = val;
+    bool pushed = false;
+    if constexpr (DIST) {
+#pragma unroll 1
+      for (int q = 0; q < a->world; ++q)
+        if (g >= L.give_lo[q] && g < L.give_hi[q]) { a->arena[q][L.e_off[k] + g] = val; pushed = true; }
+    }
+    return pushed;
+  }
+};
+
+// ---- sweep epilogues (row-per-lane; see tm_sym3_sweep) --------------------------------------------------
+struct EpiAgResidual {      // t = r - (A e + reg e), 0 on known rows of level 0
+  static constexpr int NACC = 0;
+  double* t;
+  const double* r;
+  const double* e_own;
+  const double* mask;       // null: every row is free
+  double reg;
+  struct Pre { double ri, ei, mi; };
+  __device__ __forceinline__ Pre load(int64_t i) const { return Pre{r[i], e_own[i], mask ? mask[i] : 1.0}; }
+  __device__ __forceinline__ void row(int64_t i, double sum, const Pre& pre, double (&)[1]) const {
+    t[i] = pre.mi != 0.0 ? pre.ri - (sum + reg * pre.ei) : 0.0;
+  }
+};
+
+template <bool DIST>
+struct EpiAgSmooth {        // e_out = e + omega D^-1 (r - (A e + reg e))
+  static constexpr int NACC = 0;
+  static constexpr bool WARP_UNIFORM = true;
+  const AmgLevelDev* L;
+  int k_out;
+  bool push;                // the output is gathered by another GPU's sweep
+  const double* r;
+  const double* e_own;
+  const double* mask;
+  double reg;
+  AgPut<DIST> put;
+  bool* pushed;
+  struct Pre { double ri, ei, mi; };
+  __device__ __forceinline__ Pre load(int64_t i) const { return Pre{r[i], e_own[i], mask ? mask[i] : 1.0}; }
+  __device__ __forceinline__ void row_warp(int64_t i, bool ok, double sum, const Pre& pre, double (&)[1], int lane) const {
+    const double res = (ok && pre.mi != 0.0) ? pre.ri - (sum + reg * pre.ei) : 0.0;
+    const double z = ag_dinv_apply(L->dinv, i, ok, res, lane);
+    if (ok) {
+      const double val = pre.ei + AMG_OMEGA * z;
+      if (push) { if (put(*L, k_out, i, val)) *pushed = true; }
+      else put.a->arena[put.a->rank][L->e_off[k_out] + 3 * (int64_t)L->node_off + i] = val;
+    }
+  }
+};
+
+struct EpiAgCg {            // w = A u + reg u ; acc = {r.u, w.u, r.r}
+  static constexpr int NACC = 3;
+  double* w;
+  const double* u_own;
+  const double* r;
+  double reg;
+  struct Pre { double ui, ri; };
+  __device__ __forceinline__ Pre load(int64_t i) const { return Pre{u_own[i], r[i]}; }
+  __device__ __forceinline__ void row(int64_t i, double sum, const Pre& pre, double (&acc)[3]) const {
+    const double wi = sum + reg * pre.ui;
+    w[i] = wi;
+    acc[0] += pre.ri * pre.ui;
+    acc[1] += wi * pre.ui;
+    acc[2] += pre.ri * pre.ri;
+  }
+};
+
+template <bool DIST>
+__global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
+  extern __shared__ __align__(128) unsigned char ag_smem[];
+  __shared__ double s_red[AG_WARPS][3];
+  __shared__ double s_tot[3];
+  __shared__ int s_leader;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gw = (int64_t)warp * gridDim.x + blockIdx.x;       // block-fastest: small levels spread over all SMs
+  const int64_t n_warps = (int64_t)gridDim.x * AG_WARPS;
+  const AmgLevelDev* const lv = a.lv;
+  const int NL = a.n_levels;
+  double* const arena = a.arena[a.rank];
+  AgPeerSync* const my_sync = a.sync[a.rank];
+  const double tol2 = a.sc->tol2;
+  unsigned epoch = 0, ep_red = a.epoch_red0, ep_halo = a.epoch_halo0;
+  bool pushed = false;                  // this thread stored into a peer since the last halo barrier
+  const AgPut<DIST> put{&a};
+  TmSymPipe pp;
+  tm_sym_pipe_init(pp, ag_smem, AG_WARPS, warp, lane);
+
+  // ---- barriers
+  auto local_barrier = [&]() { ag_grid_barrier(&a.bar[0], epoch); };
+  // arrive / leader / release with cross-GPU work done by warp 0 of the last-arriving block
+  auto leader_barrier = [&](bool sys_release, auto&& leader_work) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ++epoch;
+      if (sys_release) __threadfence_system(); else __threadfence();
+      const unsigned old = atomicAdd(&a.bar[0], 1u);
+      s_leader = (old == epoch * gridDim.x - 1u);
+    }
+    __syncthreads();
+    if (s_leader && warp == 0) {
+      __threadfence();
+      __syncwarp();
+      leader_work(lane);
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&a.bar[1]), "r"(epoch) : "memory");
+      }
+    }
+    if (threadIdx.x == 0) {
+      unsigned spins = 0;
+      while (ag_ld_acquire_gpu(&a.bar[1]) < epoch)
+        if (++spins > AG_SPIN_LIMIT) __trap();
+      __threadfence();
+    }
+    __syncthreads();
+  };
+  // the level's gathered vector is complete everywhere it is read
+  auto halo_barrier = [&](const AmgLevelDev& L) {
+    if constexpr (!DIST) {
+      local_barrier();
+    } else {
+      ++ep_halo;
+      const unsigned e = ep_halo;
+      const bool block_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
+      pushed = false;
+      leader_barrier(block_pushed, [&](int ln) {
+        if (ln < a.world && ln != a.rank) {
+          // every neighbour of ANY level is signalled at every halo phase, so that epochs stay in step
+          if ((a.recv_mask_all >> ln) & 1u) {
+            __threadfence_system();
+            ag_st_release_sys(&a.sync[ln]->flag_halo[a.rank], e);
+            if ((L.recv_mask >> ln) & 1u) {
+              unsigned spins = 0;
+              while (ag_ld_acquire_sys(&my_sync->flag_halo[ln]) < e)
+                if (++spins > AG_SPIN_LIMIT) __trap();
+            }
+          }
+        }
+      });
+    }
+  };
+
+  // ---- phases
+  const AmgLevelDev L0 = lv[0];
+  const int64_t n0 = 3 * (int64_t)L0.n;
+  double* const r0 = L0.r;
+  auto own = [&](const AmgLevelDev& L, int k) -> double* { return arena + L.e_off[k] + 3 * (int64_t)L.node_off; };
+  const int fin_coarsest = (AMG_COARSE_SWEEPS - 1) & 1;
+  auto fin = [&](int l) -> int { return l == NL - 1 ? fin_coarsest : 1; };
+
+  // D0: CG recurrences (or their initialisation) + pre-smoothing of level 0
+  auto phase_d0 = [&](bool first, double alpha, double beta) {
+    const double* u = own(L0, 1);
+    for (int64_t base = gw * 30; base < n0; base += n_warps * 30) {
+      const int64_t i = base + lane;
+      const bool ok = lane < 30 && i < n0;
+      double ri = 0.0;
+      if (ok) {
+        if (first) {
+          a.p[i] = 0.0;
+          a.s[i] = 0.0;
+          ri = r0[i];
+        } else {
+          const double pi = u[i] + beta * a.p[i];
+          const double si = a.w[i] + beta * a.s[i];
+          a.p[i] = pi;
+          a.s[i] = si;
+          a.x[i] += alpha * pi;
+          ri = a.mask0[i] != 0.0 ? r0[i] - alpha * si : 0.0;
+          r0[i] = ri;
+        }
+      }
+      const double z = ag_dinv_apply(L0.dinv, i, ok, ri, lane);
+      if (ok && put(L0, 0, i, AMG_OMEGA * z)) pushed = true;
+    }
+  };
+  // R_l: t = r - A e   (e = buffer 0)
+  auto phase_residual = [&](const AmgLevelDev& L, const double* mask) {
+    double dummy[1] = {0.0};
+    EpiAgResidual epi{L.t, L.r, own(L, 0), mask, a.reg};
+    tm_sym3_sweep<EpiAgResidual, false, false, true>(pp, 3 * (int64_t)L.n, L.brp, L.bval, L.bcol, arena + L.e_off[0], epi,
+                                                     dummy, gw, n_warps, lane, L.nb, TmHaloGate{});
+  };
+  // D_l (l >= 1): restriction by member lists + pre-smoothing from zero
+  auto phase_restrict = [&](const AmgLevelDev& Lf, const AmgLevelDev& L) {
+    const int64_t n = 3 * (int64_t)L.n;
+    for (int64_t base = gw * 30; base < n; base += n_warps * 30) {
+      const int64_t i = base + lane;
+      const bool ok = lane < 30 && i < n;
+      double sum = 0.0;
+      if (ok) {
+        const int64_t nd = i / 3;
+        const int c = (int)(i - 3 * nd);
+        const int32_t me = L.mptr[nd + 1];
+        for (int32_t m = L.mptr[nd]; m < me; ++m) sum += Lf.t[3 * (int64_t)L.mlist[m] + c];
+        L.r[i] = sum;
+      }
+      const double z = ag_dinv_apply(L.dinv, i, ok, sum, lane);
+      if (ok && put(L, 0, i, AMG_OMEGA * z)) pushed = true;
+    }
+  };
+  // smoothing sweep: e[k_out] = e[k_in] + omega D^-1 (r - A e[k_in])
+  auto phase_smooth = [&](const AmgLevelDev& L, int k_in, int k_out, const double* mask, bool push) {
+    double dummy[1] = {0.0};
+    EpiAgSmooth<DIST> epi{&L, k_out, push, L.r, own(L, k_in), mask, a.reg, put, &pushed};
+    tm_sym3_sweep<EpiAgSmooth<DIST>, false, false, true>(pp, 3 * (int64_t)L.n, L.brp, L.bval, L.bcol, arena + L.e_off[k_in],
+                                                         epi, dummy, gw, n_warps, lane, L.nb, TmHaloGate{});
+  };
+  // U1_l: e_l += SCALE * P e_l+1
+  auto phase_prolong = [&](const AmgLevelDev& L, const AmgLevelDev& Lc, int kc) {
+    const int64_t n = 3 * (int64_t)L.n;
+    const double* e = own(L, 0);
+    const double* ec = own(Lc, kc);
+    for (int64_t base = gw * 30; base < n; base += n_warps * 30) {
+      const int64_t i = base + lane;
+      if (lane < 30 && i < n) {
+        const int64_t nd = i / 3;
+        const int32_t ag = L.agg[nd];
+        if (ag >= 0 && put(L, 0, i, e[i] + AMG_SCALE * ec[3 * (int64_t)ag + (i - 3 * nd)])) pushed = true;
+      }
+    }
+  };
+
+  double gamma_old = 1.0, alpha_old = 1.0, rr = 0.0, alpha = 0.0, beta = 0.0;
+  long long it = 0;
+  int status = 0;   // 1 converged, 2 breakdown, 0 maxit
+  bool first = true;
+  for (;;) {
+    // ---- u = M^-1 r : V-cycle, its first phase fused with the CG recurrences
+    phase_d0(first, alpha, beta);
+    first = false;
+    halo_barrier(L0);
+    if (NL == 1) {
+      for (int k = 1; k < AMG_COARSE_SWEEPS; ++k) {
+        phase_smooth(lv[0], (k - 1) & 1, k & 1, a.mask0, true);
+        halo_barrier(L0);
+      }
+    } else {
+      for (int l = 0; l + 1 < NL; ++l) {
+        phase_residual(lv[l], l == 0 ? a.mask0 : nullptr);
+        local_barrier();
+        phase_restrict(lv[l], lv[l + 1]);
+        halo_barrier(lv[l + 1]);
+      }
+      for (int k = 1; k < AMG_COARSE_SWEEPS; ++k) {
+        phase_smooth(lv[NL - 1], (k - 1) & 1, k & 1, nullptr, true);
+        halo_barrier(lv[NL - 1]);
+      }
+      for (int l = NL - 2; l >= 0; --l) {
+        phase_prolong(lv[l], lv[l + 1], fin(l + 1));
+        halo_barrier(lv[l]);
+        phase_smooth(lv[l], 0, 1, l == 0 ? a.mask0 : nullptr, l == 0);
+        if (l == 0) halo_barrier(L0); else local_barrier();
+      }
+    }
+    // ---- w = A u, partial dots
+    double acc[3] = {0.0, 0.0, 0.0};
+    {
+      EpiAgCg epi{a.w, own(L0, 1), r0, a.reg};
+      tm_sym3_sweep<EpiAgCg, false, false, true>(pp, n0, L0.brp, L0.bval, L0.bcol, arena + L0.e_off[1], epi, acc, gw,
+                                                 n_warps, lane, L0.nb, TmHaloGate{});
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double t = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      if (lane == 0) s_red[warp][j] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (int wq = 0; wq < AG_WARPS; ++wq) t += s_red[wq][threadIdx.x];
+      a.partials[(size_t)blockIdx.x * 3 + threadIdx.x] = t;
+    }
+    // ---- reduction barrier: every GPU obtains bit-identical global sums
+    if constexpr (!DIST) {
+      local_barrier();
+      if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          double t = 0.0;
+          for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(&a.partials[(size_t)b * 3 + j]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) s_tot[j] = t;
+        }
+      }
+    } else {
+      ++ep_red;
+      const unsigned er = ep_red;
+      const int par = (int)(er & 1u);
+      leader_barrier(false, [&](int ln) {
+        double tot[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          double t = 0.0;
+          for (unsigned b = ln; b < gridDim.x; b += 32) t += __ldcg(&a.partials[(size_t)b * 3 + j]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          tot[j] = t;
+        }
+        if (ln < a.world) {        // one lane per peer: publish the local totals everywhere, collect everybody's
+          double* slot = a.sync[ln]->sums[par][a.rank];
+          slot[0] = tot[0]; slot[1] = tot[1]; slot[2] = tot[2];
+          __threadfence_system();
+          ag_st_release_sys(&a.sync[ln]->flag_red[a.rank], er);
+          unsigned spins = 0;
+          while (ag_ld_acquire_sys(&my_sync->flag_red[ln]) < er)
+            if (++spins > AG_SPIN_LIMIT) __trap();
+        }
+        __syncwarp();
+        if (ln < 3) {
+          double t = 0.0;
+          for (int q = 0; q < a.world; ++q) t += ag_ld_volatile_f64(&my_sync->sums[par][q][ln]);   // rank order
+          a.gsum[par * 4 + ln] = t;
+        }
+      });
+      if (threadIdx.x < 3) s_tot[threadIdx.x] = __ldcg(&a.gsum[par * 4 + threadIdx.x]);
+    }
+    __syncthreads();
+    const double gamma = s_tot[0], delta = s_tot[1];
+    rr = s_tot[2];
+    if (!isfinite(rr)) { status = 2; break; }
+    if (!(rr > tol2)) { status = 1; break; }
+    if (it >= a.maxit) { status = 0; break; }
+    beta = (it == 0) ? 0.0 : gamma / gamma_old;
+    const double denom = (it == 0) ? delta : delta - beta * gamma / alpha_old;
+    if (!(denom > 0.0) || !isfinite(gamma)) { status = 2; break; }
+    alpha = gamma / denom;
+    gamma_old = gamma;
+    alpha_old = alpha;
+    ++it;
+    __syncthreads();          // s_tot is rewritten by the next reduction
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.sc->iters = it;
+    a.sc->rr_final = rr;
+    a.sc->red[1] = rr;
+    a.sc->done = (status == 1);
+    a.sc->breakdown = (status == 2);
+    a.sc->pAp = (double)ep_red;          // final epochs, carried into the next solve by the host
+    a.sc->rz_old = (double)ep_halo;
+  }
+}
+
+}  // namespace
+
+size_t myc_amg_peer_tail_bytes() { return sizeof(AgPeerSync) + 256; }
+
+int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset, const int32_t* d_row_ptr,
+                    const double* d_dinv, double reg, int64_t maxit, double* d_x, cudaStream_t st, int* handled) {
+  *handled = 0;
+  AmgState* S = ctx->amg;
+  if (!S || !S->valid || S->n_rows0 != n_rows || S->row_offset0 != row_offset || S->key_rp != d_row_ptr ||
+      S->key_dinv != d_dinv || ctx->sym_owner != 1)
+    MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve(MYC_PC_AMG): call myc_amg_setup for this operator and Dirichlet set first");
+  const bool dist = ctx->world > 1;
+  if (dist) MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve(MYC_PC_AMG): multi-GPU hierarchy not installed");
+  int coop = 0;
+  MYC_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+  const size_t smem = tm_sym_smem_bytes(AG_WARPS);
+  if (ctx->amg_max_blocks_per_sm < 0) {
+    int mn = 1 << 30;
+    const void* fns[2] = {(const void*)pcg_amg_kernel<false>, (const void*)pcg_amg_kernel<true>};
+    for (const void* fn : fns) {
+      int b = 0;
+      MYC_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, AG_THREADS, smem));
+      mn = b < mn ? b : mn;
+    }
+    ctx->amg_max_blocks_per_sm = mn;
+  }
+  if (!coop || ctx->amg_max_blocks_per_sm < 1)
+    MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve(MYC_PC_AMG): cooperative launch unavailable on this device");
+  MYC_TRY(myc_ensure(ctx, ctx->vec[2], (size_t)(n_rows + 1) * sizeof(double)));
+  MYC_TRY(myc_ensure(ctx, ctx->vec[3], (size_t)(n_rows + 1) * sizeof(double)));
+  MYC_TRY(myc_ensure(ctx, ctx->vec[5], (size_t)(n_rows + 1) * sizeof(double)));
+  MYC_TRY(myc_ensure(ctx, ctx->misc, 512));
+  MYC_TRY(myc_ensure(ctx, ctx->partials, (size_t)ctx->sm_count * 16 * 4 * sizeof(double)));
+  // ---- level table
+  AmgLevelDev h_lv[AMG_MAX_LEVELS];
+  memset(h_lv, 0, sizeof(h_lv));
+  for (int l = 0; l < S->n_levels; ++l) {
+    AmgLevelHost& H = S->lv[l];
+    AmgLevelDev& D = h_lv[l];
+    D.n = (int32_t)H.n; D.node_off = (int32_t)H.node_off; D.n_global = (int32_t)H.n_global; D.nb = (int32_t)H.nb;
+    D.brp = l == 0 ? (const int32_t*)S->brp0.p : (const int32_t*)H.brp.p;
+    D.bcol = l == 0 ? (const int32_t*)ctx->sym_col.p : (const int32_t*)H.bcol.p;
+    D.bval = l == 0 ? (const double*)ctx->sym_val.p : (const double*)H.bval.p;
+    D.dinv = (const double*)H.dinv.p;
+    D.agg = l + 1 < S->n_levels ? (const int32_t*)H.agg.p : nullptr;
+    D.mptr = l > 0 ? (const int32_t*)H.mptr.p : nullptr;
+    D.mlist = l > 0 ? (const int32_t*)H.mlist.p : nullptr;
+    D.r = l == 0 ? (double*)ctx->vec[1].p : (double*)H.r.p;
+    D.t = (double*)H.t.p;
+    D.e_off[0] = H.e_off[0]; D.e_off[1] = H.e_off[1];
+  }
+  MYC_CUDA(ctx, cudaMemcpyAsync(S->lv_dev.p, h_lv, sizeof(AmgLevelDev) * S->n_levels, cudaMemcpyHostToDevice, st));
+  MYC_CUDA(ctx, cudaStreamSynchronize(st));      // h_lv is a stack array
+  unsigned* bar = (unsigned*)((char*)ctx->misc.p + 224);
+  double* gsum = (double*)((char*)ctx->misc.p + 256);
+  MYC_CUDA(ctx, cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
+  AmgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lv = (const AmgLevelDev*)S->lv_dev.p;
+  a.n_levels = S->n_levels;
+  a.arena[0] = (double*)S->arena.p;
+  a.mask0 = d_dinv;
+  a.x = d_x;
+  a.w = (double*)ctx->vec[2].p;
+  a.p = (double*)ctx->vec[3].p;
+  a.s = (double*)ctx->vec[5].p;
+  a.reg = reg;
+  a.maxit = (long long)maxit;
+  a.partials = (double*)ctx->partials.p;
+  a.bar = bar;
+  a.gsum = gsum;
+  a.sc = (PcgScalars*)ctx->scalars.p;
+  a.world = 1;
+  a.rank = 0;
+  const int64_t n_tiles = ceil_div64(n_rows / 3, TmCfgSym::NODES);
+  int grid = ctx->sm_count;
+  if (ceil_div64(n_tiles, AG_WARPS) < grid) grid = (int)ceil_div64(n_tiles, AG_WARPS);
+  if (grid < 1) grid = 1;
+  void* params[] = {&a};
+  MYC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)pcg_amg_kernel<false>, dim3(grid), dim3(AG_THREADS), params, smem, st));
+  ctx->launches++;
+  *handled = 1;
+  return MYC_OK;
+}

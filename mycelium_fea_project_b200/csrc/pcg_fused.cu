@@ -33,6 +33,7 @@
 #include "spmv.cuh"
 #include "spmv_tma.cuh"
 #include "spmv_sym3.cuh"
+#include "amg.cuh"
 
 #include <type_traits>
 
@@ -658,6 +659,8 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
     MYC_CUDA(ctx, cudaMemcpyAsync(&h_nnz, d_row_ptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MYC_CUDA(ctx, cudaStreamSynchronize(st));
     nb_total = h_nnz / 9;
+    ctx->sym_owner = 0;                       // the block view is rebuilt for THIS matrix: a multigrid hierarchy
+    if (ctx->amg) ctx->amg->valid = false;    // whose level 0 lived there is gone
     MYC_TRY(myc_ensure(ctx, ctx->sym_val, ((size_t)nb_total + 4) * 6 * sizeof(double)));
     MYC_TRY(myc_ensure(ctx, ctx->sym_col, ((size_t)nb_total + 4) * sizeof(int32_t)));
     int* bad = (int*)((char*)ctx->misc.p + 320);

@@ -41,7 +41,7 @@ __host__ __device__ constexpr size_t tm_sym_smem_bytes(int warps) {
 // One thread per owned node: pack the node's blocks.  rp/ci/v: node-block-structured CSR (local rows).
 // bval: 6 doubles per block (xx xy xz yy yz zz), bcol: DOF column of the block's first entry.
 // *bad is raised if a block is not bitwise symmetric (then the caller keeps using the CSR sweep).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 myc_sym3_convert_kernel(int64_t n_nodes, const int32_t* __restrict__ rp, const int32_t* __restrict__ ci,
                         const double* __restrict__ v, double* __restrict__ bval, int32_t* __restrict__ bcol,
                         int* __restrict__ bad) {
@@ -116,13 +116,24 @@ __device__ __forceinline__ unsigned tm_ld_acquire_sys(const unsigned* p) {
   return v;
 }
 
-// block offset of local node `nd` (clamped): the scalar CSR row pointer of its first row / 9
+// block offset of local node `nd` (clamped): the scalar CSR row pointer of its first row / 9, or -- DIRECT,
+// the multigrid levels of pcg_amg.cu -- an explicit block row pointer
+template <bool DIRECT = false>
 __device__ __forceinline__ int32_t tm_sym_node_ptr(const int32_t* __restrict__ rp, int64_t nd, int64_t n_nodes) {
-  return rp[3 * (nd < n_nodes ? nd : n_nodes)] / 9;
+  if constexpr (DIRECT) return rp[nd < n_nodes ? nd : n_nodes];
+  else return rp[3 * (nd < n_nodes ? nd : n_nodes)] / 9;
 }
 
+// Epilogues that need a whole node's rows at once (3x3 block smoothers) declare
+// `static constexpr bool WARP_UNIFORM = true` and provide row_warp(row, row_ok, sum, pre, acc, lane), which
+// ALL 32 lanes call (lane = 3 * node_in_tile + component for lane < 30), so it may shuffle.
+template <class E, class = void>
+struct tm_epi_warp_uniform { static constexpr bool value = false; };
+template <class E>
+struct tm_epi_warp_uniform<E, decltype((void)E::WARP_UNIFORM)> { static constexpr bool value = E::WARP_UNIFORM; };
+
 // One sweep of warp gw over its tiles.  x is gathered coherently (persistent solver kernel).
-template <class Epi, bool PREFETCH_NEXT, bool GATED>
+template <class Epi, bool PREFETCH_NEXT, bool GATED, bool DIRECT = false>
 __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, const int32_t* __restrict__ rp,
                                               const double* __restrict__ bval, const int32_t* __restrict__ bcol,
                                               const double* x, const Epi& epi,
@@ -144,8 +155,8 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
   // lane l < NODES holds the block range [lo_l, hi_l) of node NODES*t + l
   auto load_np = [&](int64_t t, int32_t& lo_l, int32_t& hi_l) {
     const int64_t nd = t * NODES + (lane < NODES ? lane : NODES - 1);
-    lo_l = tm_sym_node_ptr(rp, nd, n_nodes);
-    hi_l = tm_sym_node_ptr(rp, nd + 1, n_nodes);
+    lo_l = tm_sym_node_ptr<DIRECT>(rp, nd, n_nodes);
+    hi_l = tm_sym_node_ptr<DIRECT>(rp, nd + 1, n_nodes);
   };
   auto issue = [&](int s, int32_t lo, int32_t hi) {
     int32_t a0, a1;
@@ -268,7 +279,8 @@ __device__ __forceinline__ void tm_sym3_sweep(TmSymPipe& pp, int64_t n_rows, con
         }
       }
     }
-    if (row_ok) epi.row(r0 + lane, sum, pre, acc);
+    if constexpr (tm_epi_warp_uniform<Epi>::value) epi.row_warp(r0 + lane, row_ok, sum, pre, acc, lane);
+    else if (row_ok) epi.row(r0 + lane, sum, pre, acc);
     cur_lo = nxt_lo; cur_hi = nxt_hi;
     nxt_lo = nn_lo; nxt_hi = nn_hi;
   }

@@ -149,6 +149,9 @@ class DirichletSystem:
                                        # (n_blocks, R(R+1)/2) for "block6" / "block12" (R = 6 / 12 rows per block)
     reg: float = REGULARISATION
     binv_kind: str | None = None       # which preconditioner ``binv`` belongs to
+    precond: str = "jacobi"            # the preconditioner this system was prepared for ("amg" falls back to
+                                       # "block6" when the multigrid hierarchy is not applicable, see apply_dirichlet)
+    amg_levels: int = 0                # levels of the multigrid hierarchy (0: none)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -177,8 +180,11 @@ def assemble(ctx: Context, mesh: DeviceMesh, E, A, I, node_range=None) -> Device
 
 def apply_dirichlet(ctx: Context, K: DeviceCSR, known_dofs: torch.Tensor, known_vals: torch.Tensor,
                     reg=REGULARISATION, block3=False, precond=None) -> DirichletSystem:
-    """``precond`` ("jacobi", "block3", "block6", "block12") selects which block inverses are built next
-    to the Jacobi diagonal; ``block3=True`` is the older spelling of precond="block3"."""
+    """``precond`` ("jacobi", "block3", "block6", "block12", "amg") selects what is built next to the Jacobi
+    diagonal: block inverses, or the aggregation-multigrid hierarchy (kept inside the context; it belongs to
+    the LAST system prepared with precond="amg").  "amg" needs a node-block-structured, blockwise symmetric K
+    and node-complete Dirichlet sets; otherwise the system is prepared for "block6" (``.precond`` tells).
+    ``block3=True`` is the older spelling of precond="block3"."""
     if precond is None:
         precond = "block3" if block3 else "jacobi"
     if precond not in _lib.PRECONDITIONERS:
@@ -191,6 +197,14 @@ def apply_dirichlet(ctx: Context, K: DeviceCSR, known_dofs: torch.Tensor, known_
                                          _ptr(K.val), _ptr(known_dofs), _ptr(known_vals), known_dofs.shape[0],
                                          float(reg), _ptr(ubc), _ptr(rhs), _ptr(dinv), _stream()))
     binv = None
+    amg_levels = 0
+    if precond == "amg":
+        lv = C.c_int(0)
+        check(ctx.h, lib.myc_amg_setup(ctx.h, K.n_rows, K.n_cols, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx),
+                                       _ptr(K.val), _ptr(dinv), float(reg), C.byref(lv), _stream()))
+        amg_levels = int(lv.value)
+        if amg_levels == 0:
+            precond = "block6" if K.row_offset % 6 == 0 else "block3"
     if precond == "block3":
         binv = torch.empty((K.n_rows // 3, 9), dtype=torch.float64, device=ctx.device)
         check(ctx.h, lib.myc_block3_inverse(ctx.h, K.n_rows, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx),
@@ -203,7 +217,8 @@ def apply_dirichlet(ctx: Context, K: DeviceCSR, known_dofs: torch.Tensor, known_
         binv = torch.empty((n_blocks, size // n_blocks if n_blocks else 0), dtype=torch.float64, device=ctx.device)
         check(ctx.h, lib.myc_block_inverse_packed(ctx.h, npb, K.n_rows, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx),
                                                   _ptr(K.val), _ptr(dinv), float(reg), _ptr(binv), _stream()))
-    return DirichletSystem(ubc, rhs, dinv, binv, float(reg), precond if binv is not None else None)
+    return DirichletSystem(ubc, rhs, dinv, binv, float(reg), precond if binv is not None else None, precond,
+                           amg_levels)
 
 
 def spmv(ctx: Context, K: DeviceCSR, x: torch.Tensor, out: torch.Tensor | None = None):
@@ -218,8 +233,13 @@ def pcg(ctx: Context, K: DeviceCSR, sys: DirichletSystem, x0: torch.Tensor | Non
         rtol=1e-10, atol=0.0, maxit=1_000_000, raise_on_maxit=True):
     """Returns (x, iterations, relres).  x is the solution on free rows (0 on known rows)."""
     x = torch.zeros((K.n_rows,), dtype=torch.float64, device=ctx.device) if x0 is None else x0
+    if precond == "amg" and sys.precond != "amg":
+        precond = sys.precond                          # hierarchy not applicable: the system was prepared for a fallback
     pc = _lib.PRECONDITIONERS[precond]
-    if pc != _lib.MYC_PC_JACOBI and (sys.binv is None or sys.binv_kind != precond):
+    if pc == _lib.MYC_PC_AMG:
+        if sys.precond != "amg":
+            raise ValueError("amg preconditioner needs apply_dirichlet(..., precond='amg')")
+    elif pc != _lib.MYC_PC_JACOBI and (sys.binv is None or sys.binv_kind != precond):
         raise ValueError(f"{precond} preconditioner needs apply_dirichlet(..., precond={precond!r})")
     iters, relres = C.c_int64(0), C.c_double(0.0)
     _hint(ctx, K)
@@ -228,6 +248,27 @@ def pcg(ctx: Context, K: DeviceCSR, sys: DirichletSystem, x0: torch.Tensor | Non
                            float(atol), int(maxit), _ptr(x), C.byref(iters), C.byref(relres), _stream())
     check(ctx.h, rc, allow_not_converged=not raise_on_maxit)
     return x, int(iters.value), float(relres.value)
+
+
+def amg_levels(ctx: Context):
+    """[(nodes, blocks)] per level of the context's current multigrid hierarchy, and its setup time in ms."""
+    out = (C.c_int64 * 4)()
+    check(ctx.h, lib.myc_amg_level_info(ctx.h, 0, out, None, _stream()))
+    n_levels, setup_ms = int(out[2]), out[3] / 1e3
+    levels = []
+    for l in range(n_levels):
+        check(ctx.h, lib.myc_amg_level_info(ctx.h, l, out, None, _stream()))
+        levels.append((int(out[0]), int(out[1])))
+    return levels, setup_ms
+
+
+def amg_aggregates(ctx: Context, level: int) -> torch.Tensor:
+    """node -> aggregate map of ``level`` (int32, -1 = not represented on the next level)."""
+    out = (C.c_int64 * 4)()
+    check(ctx.h, lib.myc_amg_level_info(ctx.h, level, out, None, _stream()))
+    agg = torch.empty((int(out[0]),), dtype=torch.int32, device=ctx.device)
+    check(ctx.h, lib.myc_amg_level_info(ctx.h, level, out, _ptr(agg), _stream()))
+    return agg
 
 
 def true_residual(ctx: Context, K: DeviceCSR, sys: DirichletSystem, x: torch.Tensor) -> float:
