@@ -164,12 +164,21 @@ int myc_block_inverse_packed(myc_ctx* ctx, int nodes_per_block, int64_t n_rows, 
  * the same d_row_ptr / d_dinv.  The hierarchy stays valid for further right-hand sides on the same operator
  * and Dirichlet set.  *h_out_levels = 0 means "not applicable" (the CSR lacks the 3x3 node-block structure or
  * blockwise symmetry, or a node has only some of its DOFs prescribed): use a Jacobi-type preconditioner.
- * myc_amg_level_info: out[0] nodes, out[1] blocks of `level`, out[2] number of levels, out[3] setup time (us);
+ * Several GPUs (after myc_dist_init + myc_dist_set_plan; the row block must be the installed partition's):
+ * COLLECTIVE -- every rank calls it with its rows, and every rank gets the same *h_out_levels.  Aggregates are
+ * formed inside a rank, levels stay row-partitioned with the correction vectors exchanged through NVLink peer
+ * memory; a level with at most 65,536 nodes over all ranks (MYC_AMG_REPLICATE_NODES) is gathered onto every
+ * rank and processed redundantly from there down.  This is the GPU path's form of the reference's PCBJACOBI /
+ * GAMG under mpirun (src/fea_petsc_parallel.cpp:330-351).
+ * myc_amg_level_info (this rank's part): out[0] nodes, out[1] blocks of `level`, out[2] number of levels,
+ * out[3] setup time (us), out[4] global id of the first held node, out[5] nodes of the level over all ranks,
+ * out[6] 0 = row-partitioned (or single GPU) / 1 = first replicated level / 2 = replicated, out[7] = offset
+ * already added to the aggregate map so that it indexes the next level from this rank's first node there;
  * d_out_agg (may be NULL): the level's node -> aggregate map (int32, -1 = not represented on the next level). */
 int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset,
                   const int32_t* d_row_ptr, const int32_t* d_col_idx, const double* d_val,
                   const double* d_dinv, double reg, int* h_out_levels, void* stream);
-int myc_amg_level_info(myc_ctx* ctx, int level, int64_t* h_out4, int32_t* d_out_agg, void* stream);
+int myc_amg_level_info(myc_ctx* ctx, int level, int64_t* h_out8, int32_t* d_out_agg, void* stream);
 
 /* Structure parity aid: the explicit reduced matrix K[free][:,free] the reference builds
  * (src/fea_solver.py:118), as CSR over the compacted free numbering.  Two-phase like assembly:
@@ -275,7 +284,10 @@ int myc_allgather_owned(myc_ctx* ctx, double* d_x_global, void* stream);
  * H2D of the mesh and BCs, assembly, Dirichlet elimination, PCG, reactions, D2H of U.
  * Equivalent to  K = assemble_global_stiffness(..); U = solve_system(K, known_dofs, known_vals);
  * F = K @ U  (src/fea_solver.py:220-257).  Single GPU.  h_out_U: n_dof doubles.  h_react_idx
- * (may be NULL/0): DOF indices whose reactions are summed into h_out_force.
+ * (may be NULL/0): DOF indices whose reactions are summed into h_out_force.  precond = MYC_PC_AMG builds the
+ * multigrid hierarchy inside the call (and uses MYC_PC_BLOCK6 where it is not applicable).  Host buffers may
+ * be pageable or pinned (pinned: the copies run at full PCIe speed).  h_out_ms_assemble covers H2D + assembly,
+ * h_out_ms_solve everything after it (Dirichlet, preconditioner setup, PCG, reactions, D2H).
  */
 int myc_load_case_host(myc_ctx* ctx, const double* h_coords, const int32_t* h_n1, const int32_t* h_n2,
                        const uint8_t* h_active, int64_t n_elem, int64_t n_nodes, double E, double A,

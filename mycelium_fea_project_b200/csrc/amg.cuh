@@ -9,8 +9,20 @@
 //
 // Level l:  n nodes owned by this rank (global ids node_off .. node_off+n), block row pointer brp, block columns
 // bcol = 3 * GLOBAL node id, values bval (xx xy xz yy yz zz), dinv = symmetric inverse of (diagonal block + reg I).
-// agg maps a node to its aggregate (local index on level l+1, -1 = not represented there); mptr/mlist list the
-// members of each node of level l on level l-1 (restriction gathers, so it needs no atomics).
+// agg maps a node to its aggregate (index on level l+1 relative to that level's node_off, -1 = not represented
+// there); mptr/mlist list the members of each node of level l on level l-1 (restriction gathers, so it needs no
+// atomics).
+//
+// Several GPUs (one process per GPU, rows partitioned by contiguous node ranges -- the PETSc MPIAIJ layout of
+// src/fea_petsc_parallel.cpp:236): aggregates are formed inside a rank, so level l+1 inherits the partition and
+// restriction / prolongation need no communication; the correction vectors a sweep gathers are kept at the
+// level's GLOBAL length in every rank's IPC-shared arena and the rows a neighbour reads are stored there
+// directly (NVLink P2P).  A level with at most amg_replicate_nodes nodes over all ranks is REPLICATED instead:
+// its operator is all-gathered once at setup, every rank then coarsens and smooths it in full, redundantly and
+// bit-identically, and from there down the V-cycle needs no cross-GPU barrier at all (and aggregates are no
+// longer confined to a rank, so the coarsest level ends up as small as on one GPU).  The one exchange at the
+// seam: every rank restricts onto its own aggregates and stores that part of the right-hand side into
+// everybody's arena.
 // Algorithm and constants are restated in numpy in oracle/amg_oracle.py, which the tests compare with.
 #pragma once
 #include "common.cuh"
@@ -41,12 +53,22 @@ struct AmgLevelDev {                     // what the solver kernel reads (device
   int64_t give_lo[MYC_MAX_WORLD];        // DOF ranges [lo, hi) (global, this level) of MY rows that peer q gathers
   int64_t give_hi[MYC_MAX_WORLD];
   unsigned recv_mask;                    // bit q: this rank gathers rows of peer q on this level
+  int32_t replicated;                    // 0: rows partitioned over the ranks (or one GPU); 1: first replicated level
+                                         // (the seam: r is assembled from every rank's part); 2: replicated, deeper
+  int32_t own_lo, own_n;                 // seam level: the aggregates of THIS rank (global ids own_lo .. own_lo+own_n);
+                                         // mptr / mlist describe exactly those
+  int64_t r_off;                         // seam level: offset of r inside every rank's arena (r then points there)
 };
 
 struct AmgLevelHost {
   int64_t n = 0, nb = 0, n_global = 0, node_off = 0;
+  int replicated = 0;
+  int64_t own_lo = 0, own_n = 0;         // seam level: this rank's aggregates
+  int64_t agg_shift = 0;                 // what was added to this level's agg[] so that it indexes level l+1 relative
+                                         // to that level's node_off (non-zero only above the seam)
   DevBuf brp, bcol, bval, dinv, agg, mptr, mlist, r, t;
   int64_t e_off[2] = {0, 0};
+  int64_t r_off = -1;                    // seam level: r lives in the arena
   int64_t need_lo[MYC_MAX_WORLD] = {0}, need_hi[MYC_MAX_WORLD] = {0};     // node ranges (global, this level)
   int64_t give_lo[MYC_MAX_WORLD] = {0}, give_hi[MYC_MAX_WORLD] = {0};
 };
@@ -63,6 +85,9 @@ struct AmgState {
   DevBuf lv_dev;                         // AmgLevelDev[n_levels]
   DevBuf brp0;                           // level 0 block row pointer (rp[3 i] / 9)
   DevBuf act0;                           // level 0 activity (1 = node with three free DOFs), uint8 per node
+  DevBuf act_global;                     // several GPUs: level 0 activity of every node (global ids)
+  DevBuf agg_global;                     // several GPUs: global aggregate id of every node of the level being coarsened
+  int world = 1;                         // ranks the hierarchy was built for
   DevBuf work[6];                        // best / paired / root / keep / flags / scan output (int32 x n)
   DevBuf arena;                          // single GPU: the gathered correction vectors of all levels
   int64_t arena_doubles = 0;             // doubles the e vectors of all levels need
@@ -71,6 +96,7 @@ struct AmgState {
 
 // amg_setup.cu
 int myc_amg_destroy(myc_ctx* ctx);
+void* myc_amg_peer_sync_of(const myc_ctx* ctx, int q);   // the AgPeerSync block behind rank q's arena
 // pcg_amg.cu: runs the AMG-PCG iteration loop as one persistent kernel; on entry r = b - A x0 is in ctx->vec[1]
 // and sc->tol2 is set (pcg.cu).  *handled = 0: not applicable (no valid hierarchy, no cooperative launch).
 int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t row_offset, const int32_t* d_row_ptr,

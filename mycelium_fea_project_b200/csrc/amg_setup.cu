@@ -216,6 +216,63 @@ am_dinv_kernel(int64_t n, int64_t node_off, const int32_t* __restrict__ brp, con
   }
 }
 
+// ---- several GPUs -------------------------------------------------------------------------------------------
+// own section of the level's global aggregate map (global aggregate id, or -1)
+__global__ void __launch_bounds__(AM_THREADS)
+am_agg_global_kernel(int64_t n, int64_t node_off, const int32_t* __restrict__ agg, int32_t cnode_off,
+                     int32_t* __restrict__ agg_global) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    agg_global[node_off + i] = agg[i] >= 0 ? cnode_off + agg[i] : -1;
+}
+
+// a[i] += shift where a[i] >= 0
+__global__ void __launch_bounds__(AM_THREADS)
+am_shift_kernel(int64_t n, int32_t* __restrict__ a, int32_t shift) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (a[i] >= 0) a[i] += shift;
+}
+
+// own section of a replicated level's block row pointer; every rank also writes the end marker
+__global__ void __launch_bounds__(AM_THREADS)
+am_brp_section_kernel(int64_t n_c, int64_t cnode_off, const int32_t* __restrict__ brp_local, int32_t blk_off,
+                      int64_t n_c_global, int32_t nb_global, int32_t* __restrict__ brp_full) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_c; i += (int64_t)gridDim.x * blockDim.x)
+    brp_full[cnode_off + i] = blk_off + brp_local[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) brp_full[n_c_global] = nb_global;
+}
+
+struct AmOffsets { int64_t off[MYC_MAX_WORLD + 1]; int world, rank; };
+// per peer q: the half-open range of q's nodes that appear as block columns of this rank's rows
+// (integer min / max: order independent).  lo[] preset to INT_MAX, hi[] to 0.
+__global__ void __launch_bounds__(AM_THREADS)
+am_halo_range_kernel(int64_t nb, const int32_t* __restrict__ bcol, AmOffsets o, int32_t* __restrict__ lo, int32_t* __restrict__ hi) {
+  int32_t mylo[MYC_MAX_WORLD], myhi[MYC_MAX_WORLD];
+#pragma unroll
+  for (int q = 0; q < MYC_MAX_WORLD; ++q) { mylo[q] = 0x7fffffff; myhi[q] = 0; }
+  const int64_t own_lo = o.off[o.rank], own_hi = o.off[o.rank + 1];
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t c = bcol[b] / 3;
+    if (c >= own_lo && c < own_hi) continue;
+#pragma unroll
+    for (int q = 0; q < MYC_MAX_WORLD; ++q)
+      if (q < o.world && c >= o.off[q] && c < o.off[q + 1]) {
+        mylo[q] = c < mylo[q] ? c : mylo[q];
+        myhi[q] = c + 1 > myhi[q] ? c + 1 : myhi[q];
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < MYC_MAX_WORLD; ++q) {
+    int32_t l = mylo[q], h = myhi[q];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const int32_t l2 = __shfl_xor_sync(0xffffffffu, l, d), h2 = __shfl_xor_sync(0xffffffffu, h, d);
+      l = l2 < l ? l2 : l;
+      h = h2 > h ? h2 : h;
+    }
+    if ((threadIdx.x & 31) == 0 && h > 0) { atomicMin(&lo[q], l); atomicMax(&hi[q], h); }
+  }
+}
+
 int am_bits_for(int64_t n) {
   int b = 1;
   while (((int64_t)1 << b) < n) ++b;
@@ -224,15 +281,87 @@ int am_bits_for(int64_t n) {
 
 }  // namespace
 
+size_t myc_amg_peer_tail_bytes();      // pcg_amg.cu: the AgPeerSync block behind the arena
+
+namespace {
+void am_drop(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+void am_close_peers(myc_ctx* ctx) {
+  for (int q = 0; q < MYC_MAX_WORLD; ++q) {
+    if (ctx->amg_peer_base[q] && ctx->amg_peer_base[q] != ctx->amg_peer_own) cudaIpcCloseMemHandle(ctx->amg_peer_base[q]);
+    ctx->amg_peer_base[q] = nullptr;
+  }
+  if (ctx->amg_peer_own) cudaFree(ctx->amg_peer_own);
+  ctx->amg_peer_own = nullptr;
+  ctx->amg_peer_cap = 0;
+}
+
+// Several GPUs: the vector arena lives in one IPC-shared allocation per rank (vectors, then the AgPeerSync block).
+// Collective; `doubles` is the same number on every rank, so every rank takes the same branch.  *ok = 0 if a peer
+// mapping could not be opened on SOME rank (then no rank uses the multigrid path).
+int am_peer_ensure(myc_ctx* ctx, int64_t doubles, cudaStream_t st, int* ok) {
+  *ok = 1;
+  if (ctx->amg_peer_own && ctx->amg_peer_cap >= doubles) return MYC_OK;
+  MYC_CUDA(ctx, cudaDeviceSynchronize());
+  // nobody may still be storing into the old buffers: all ranks pass this exchange before any of them frees
+  int64_t token = 1, all[MYC_MAX_WORLD];
+  MYC_TRY(myc_dist_allgather_host_i64(ctx, &token, 1, all, st));
+  am_close_peers(ctx);
+  const int64_t cap = doubles + doubles / 4 + 1024;
+  const size_t vec_bytes = ((size_t)cap * sizeof(double) + 255) / 256 * 256;
+  const size_t bytes = vec_bytes + myc_amg_peer_tail_bytes();
+  MYC_CUDA(ctx, cudaMalloc(&ctx->amg_peer_own, bytes));
+  MYC_CUDA(ctx, cudaMemset(ctx->amg_peer_own, 0, bytes));
+  MYC_CUDA(ctx, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  MYC_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->amg_peer_own));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  unsigned char handles[64 * MYC_MAX_WORLD];
+  MYC_TRY(myc_dist_allgather_host_64b(ctx, &h, handles, st));
+  int64_t mine_ok = 1;
+  for (int q = 0; q < ctx->world; ++q) {
+    if (q == ctx->rank) { ctx->amg_peer_base[q] = ctx->amg_peer_own; continue; }
+    cudaIpcMemHandle_t hq;
+    memcpy(&hq, handles + 64 * (size_t)q, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      mine_ok = 0;
+      break;
+    }
+    ctx->amg_peer_base[q] = p;
+  }
+  MYC_TRY(myc_dist_allgather_host_i64(ctx, &mine_ok, 1, all, st));
+  for (int q = 0; q < ctx->world; ++q) if (!all[q]) *ok = 0;
+  if (!*ok) {
+    am_close_peers(ctx);
+    return MYC_OK;
+  }
+  ctx->amg_peer_cap = cap;
+  ctx->amg_epoch_red = ctx->amg_epoch_halo = 0;      // the flag block is new (zeroed) on every rank
+  return MYC_OK;
+}
+}  // namespace
+
+void* myc_amg_peer_sync_of(const myc_ctx* ctx, int q) {
+  const size_t vec_bytes = ((size_t)ctx->amg_peer_cap * sizeof(double) + 255) / 256 * 256;
+  return (char*)ctx->amg_peer_base[q] + vec_bytes;
+}
+
 int myc_amg_destroy(myc_ctx* ctx) {
+  am_close_peers(ctx);
   AmgState* s = ctx->amg;
   if (!s) return MYC_OK;
-  auto drop = [](DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
   for (AmgLevelHost& L : s->lv) {
-    drop(L.brp); drop(L.bcol); drop(L.bval); drop(L.dinv); drop(L.agg); drop(L.mptr); drop(L.mlist); drop(L.r); drop(L.t);
+    am_drop(L.brp); am_drop(L.bcol); am_drop(L.bval); am_drop(L.dinv); am_drop(L.agg); am_drop(L.mptr); am_drop(L.mlist);
+    am_drop(L.r); am_drop(L.t);
   }
-  drop(s->lv_dev); drop(s->brp0); drop(s->arena); drop(s->act0);
-  for (DevBuf& b : s->work) drop(b);
+  am_drop(s->lv_dev); am_drop(s->brp0); am_drop(s->arena); am_drop(s->act0); am_drop(s->act_global); am_drop(s->agg_global);
+  for (DevBuf& b : s->work) am_drop(b);
   delete s;
   ctx->amg = nullptr;
   return MYC_OK;
@@ -249,13 +378,20 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   AmgState* S = ctx->amg;
   S->valid = false;
   S->n_levels = 0;
-  // the hierarchy is built on the symmetric 3x3 node-block view of K: needs the node-block structure
-  if (!ctx->csr_block3 || n_rows % 3 != 0 || row_offset % 3 != 0 || n_rows == 0 ||
-      (((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) != 0)
-    return MYC_OK;
-  if (ctx->world > 1) return MYC_OK;        // the row-partitioned hierarchy is set up by myc_amg_setup_dist
+  const int world = ctx->world, rank = ctx->rank;
+  const bool dist = world > 1;
+  if (dist && (world > MYC_MAX_WORLD || !ctx->comm || !ctx->node_offsets))
+    MYC_FAIL(ctx, MYC_ERR_STATE, "amg_setup: multi-GPU context without communicator / partition (myc_dist_init, myc_dist_set_plan)");
+  if (dist && (3 * ctx->node_offsets[rank] != row_offset || 3 * ctx->node_offsets[rank + 1] != row_offset + n_rows ||
+               3 * ctx->node_offsets[world] != n_cols_global))
+    MYC_FAIL(ctx, MYC_ERR_STATE, "amg_setup: the row block does not match the installed partition");
   MYC_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
+  // The hierarchy is built on the symmetric 3x3 node-block view of K: needs the node-block structure.  On several
+  // GPUs the verdict is collective (every rank must take the same path), so local findings are only recorded here.
+  int64_t local_ok = (ctx->csr_block3 && n_rows % 3 == 0 && row_offset % 3 == 0 && (dist || n_rows > 0) &&
+                      (n_rows == 0 || (((uintptr_t)d_col_idx | (uintptr_t)d_val) & 15u) == 0)) ? 1 : 0;
+  if (!dist && !local_ok) return MYC_OK;
   ctx->plan_valid = false;                  // the sort buffers of the assembly plan are reused below
   MYC_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
   const int64_t n0 = n_rows / 3;
@@ -263,39 +399,55 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   MYC_TRY(myc_ensure(ctx, ctx->misc, 512));
   int* bad = (int*)((char*)ctx->misc.p + 320);
   int64_t* d_total = (int64_t*)((char*)ctx->misc.p + 64);
+  int32_t* d_range = (int32_t*)((char*)ctx->misc.p + 384);     // [2][MYC_MAX_WORLD] halo ranges of one level
 
   // ---- level 0: symmetric block view of K (also what the solver sweeps), block row pointer, activity
-  int32_t h_nnz = 0;
-  MYC_CUDA(ctx, cudaMemcpyAsync(&h_nnz, d_row_ptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  MYC_CUDA(ctx, cudaStreamSynchronize(st));
-  const int64_t nb0 = h_nnz / 9;
-  MYC_TRY(myc_ensure(ctx, ctx->sym_val, ((size_t)nb0 + 4) * 6 * sizeof(double)));
-  MYC_TRY(myc_ensure(ctx, ctx->sym_col, ((size_t)nb0 + 4) * sizeof(int32_t)));
-  MYC_TRY(myc_ensure(ctx, S->brp0, (size_t)(n0 + 1) * sizeof(int32_t)));
-  MYC_TRY(myc_ensure(ctx, S->act0, (size_t)(n0 + 1)));
-  MYC_CUDA(ctx, cudaMemsetAsync(bad, 0, 2 * sizeof(int), st));
-  myc_sym3_convert_kernel<<<grid_for(ctx, ceil_div64(n0, 256), 8), 256, 0, st>>>(
-      n0, d_row_ptr, d_col_idx, d_val, (double*)ctx->sym_val.p, (int32_t*)ctx->sym_col.p, bad);
-  MYC_LAUNCHED(ctx);
-  am_level0_kernel<<<grid_for(ctx, ceil_div64(n0 + 1, AM_THREADS), 8), AM_THREADS, 0, st>>>(
-      n0, d_row_ptr, d_dinv, (int32_t*)S->brp0.p, (uint8_t*)S->act0.p, bad + 1);
-  MYC_LAUNCHED(ctx);
-  int* h_bad = (int*)(h_pin + 8);
-  MYC_CUDA(ctx, cudaMemcpyAsync(h_bad, bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  MYC_CUDA(ctx, cudaStreamSynchronize(st));
-  if (h_bad[0] || h_bad[1]) return MYC_OK;  // K not blockwise symmetric, or a node with a partial Dirichlet set
+  int64_t nb0 = 0;
+  if (local_ok) {
+    int32_t h_nnz = 0;
+    MYC_CUDA(ctx, cudaMemcpyAsync(&h_nnz, d_row_ptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaStreamSynchronize(st));
+    nb0 = h_nnz / 9;
+    MYC_TRY(myc_ensure(ctx, ctx->sym_val, ((size_t)nb0 + 4) * 6 * sizeof(double)));
+    MYC_TRY(myc_ensure(ctx, ctx->sym_col, ((size_t)nb0 + 4) * sizeof(int32_t)));
+    MYC_TRY(myc_ensure(ctx, S->brp0, (size_t)(n0 + 1) * sizeof(int32_t)));
+    MYC_TRY(myc_ensure(ctx, S->act0, (size_t)(n0 + 1)));
+    MYC_CUDA(ctx, cudaMemsetAsync(bad, 0, 2 * sizeof(int), st));
+    myc_sym3_convert_kernel<<<grid_for(ctx, ceil_div64(n0, 256), 8), 256, 0, st>>>(
+        n0, d_row_ptr, d_col_idx, d_val, (double*)ctx->sym_val.p, (int32_t*)ctx->sym_col.p, bad);
+    MYC_LAUNCHED(ctx);
+    am_level0_kernel<<<grid_for(ctx, ceil_div64(n0 + 1, AM_THREADS), 8), AM_THREADS, 0, st>>>(
+        n0, d_row_ptr, d_dinv, (int32_t*)S->brp0.p, (uint8_t*)S->act0.p, bad + 1);
+    MYC_LAUNCHED(ctx);
+    int* h_bad = (int*)(h_pin + 8);
+    MYC_CUDA(ctx, cudaMemcpyAsync(h_bad, bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_bad[0] || h_bad[1]) local_ok = 0;   // K not blockwise symmetric, or a node with a partial Dirichlet set
+  }
+  int64_t h_all[32 * MYC_MAX_WORLD];
+  MYC_TRY(myc_dist_allgather_host_i64(ctx, &local_ok, 1, h_all, st));
+  for (int q = 0; q < world; ++q) if (!h_all[q]) return MYC_OK;
   ctx->sym_owner = 1;                       // sym_val / sym_col now belong to this hierarchy
+  S->world = world;
 
-  for (DevBuf& w : S->work) MYC_TRY(myc_ensure(ctx, w, (size_t)(n0 + 2) * sizeof(int32_t)));
-  int32_t* best = (int32_t*)S->work[0].p;
-  int32_t* paired = (int32_t*)S->work[1].p;
-  int32_t* root = (int32_t*)S->work[2].p;
-  int32_t* keep = (int32_t*)S->work[3].p;
-  int32_t* flag = (int32_t*)S->work[4].p;   // regrown below when a level has more blocks than level 0 has nodes
+  // partition of the level being coarsened: rank q owns the nodes [lvl_off[q], lvl_off[q+1]) of the level
+  int64_t lvl_off[MYC_MAX_WORLD + 1] = {0};
+  if (dist) for (int q = 0; q <= world; ++q) lvl_off[q] = ctx->node_offsets[q];
+  else lvl_off[1] = n0;
+  const uint8_t* act_global = nullptr;
+  if (dist) {                               // activity of the remote ends of the cut blocks (keep rule)
+    const int64_t ng = n_cols_global / 3;
+    MYC_TRY(myc_ensure(ctx, S->act_global, (size_t)ng + 16));
+    if (n0 > 0)
+      MYC_CUDA(ctx, cudaMemcpyAsync((uint8_t*)S->act_global.p + lvl_off[rank], S->act0.p, (size_t)n0, cudaMemcpyDeviceToDevice, st));
+    MYC_TRY(myc_dist_allgatherv(ctx, S->act_global.p, lvl_off, st));
+    act_global = (const uint8_t*)S->act_global.p;
+  }
 
   // level 0 views (not owned by the level: K's block view lives in ctx->sym_*)
   AmgLevelHost* L = &S->lv[0];
   L->n = n0; L->nb = nb0; L->n_global = n_cols_global / 3; L->node_off = row_offset / 3;
+  L->replicated = 0; L->own_lo = L->own_n = 0; L->agg_shift = 0; L->r_off = -1;
   const int32_t* brp = (const int32_t*)S->brp0.p;
   const int32_t* bcol = (const int32_t*)ctx->sym_col.p;
   const double* bval = (const double*)ctx->sym_val.p;
@@ -304,20 +456,59 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   for (;;) {
     L = &S->lv[lv];
     const int64_t n = L->n, nb = L->nb;
+    const bool part = dist && !L->replicated;        // this level's rows are partitioned over the ranks
     const int g_n = grid_for(ctx, ceil_div64(n, AM_THREADS), 8);
+    for (int q = 0; q < MYC_MAX_WORLD; ++q) L->need_lo[q] = L->need_hi[q] = L->give_lo[q] = L->give_hi[q] = 0;
     MYC_TRY(myc_ensure(ctx, L->dinv, (size_t)(n + 1) * 6 * sizeof(double)));
     am_dinv_kernel<<<g_n, AM_THREADS, 0, st>>>(n, L->node_off, brp, bcol, bval, act, reg, (double*)L->dinv.p);
     MYC_LAUNCHED(ctx);
+    if (part) {
+      // ---- halo plan of the level: which of q's rows do my blocks gather, and (transposed) who gathers mine
+      AmOffsets o;
+      for (int q = 0; q <= MYC_MAX_WORLD; ++q) o.off[q] = q <= world ? lvl_off[q] : lvl_off[world];
+      o.world = world; o.rank = rank;
+      int32_t h_range[2 * MYC_MAX_WORLD];
+      for (int q = 0; q < MYC_MAX_WORLD; ++q) { h_range[q] = 0x7fffffff; h_range[MYC_MAX_WORLD + q] = 0; }
+      MYC_CUDA(ctx, cudaMemcpyAsync(d_range, h_range, sizeof(h_range), cudaMemcpyHostToDevice, st));
+      if (nb > 0) {
+        am_halo_range_kernel<<<grid_for(ctx, ceil_div64(nb, AM_THREADS), 8), AM_THREADS, 0, st>>>(nb, bcol, o, d_range,
+                                                                                                  d_range + MYC_MAX_WORLD);
+        MYC_LAUNCHED(ctx);
+      }
+      MYC_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(h_range), cudaMemcpyDeviceToHost, st));
+      MYC_CUDA(ctx, cudaStreamSynchronize(st));
+      int64_t mine[2 * MYC_MAX_WORLD];
+      for (int q = 0; q < MYC_MAX_WORLD; ++q) {
+        const bool any = q < world && q != rank && h_range[MYC_MAX_WORLD + q] > 0;
+        mine[q] = L->need_lo[q] = any ? h_range[q] : 0;
+        mine[MYC_MAX_WORLD + q] = L->need_hi[q] = any ? h_range[MYC_MAX_WORLD + q] : 0;
+      }
+      MYC_TRY(myc_dist_allgather_host_i64(ctx, mine, 2 * MYC_MAX_WORLD, h_all, st));
+      for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        L->give_lo[q] = h_all[q * 2 * MYC_MAX_WORLD + rank];
+        L->give_hi[q] = h_all[q * 2 * MYC_MAX_WORLD + MYC_MAX_WORLD + rank];
+      }
+    }
     if (lv + 1 >= AMG_MAX_LEVELS || L->n_global <= AMG_MIN_NODES) break;
-    // ---- aggregates
+    // ---- aggregates (rank-local on a partitioned level)
+    for (int k = 0; k < 4; ++k) MYC_TRY(myc_ensure(ctx, S->work[k], (size_t)(n + 2) * sizeof(int32_t)));
+    MYC_TRY(myc_ensure(ctx, S->work[4], (size_t)((nb > n ? nb : n) + 2) * sizeof(int32_t)));
+    MYC_TRY(myc_ensure(ctx, S->work[5], (size_t)((nb > n ? nb : n) + 2) * sizeof(int32_t)));
+    int32_t* best = (int32_t*)S->work[0].p;
+    int32_t* paired = (int32_t*)S->work[1].p;
+    int32_t* root = (int32_t*)S->work[2].p;
+    int32_t* keep = (int32_t*)S->work[3].p;
+    int32_t* flag = (int32_t*)S->work[4].p;
+    int32_t* uidx = (int32_t*)S->work[5].p;
     am_propose_kernel<<<g_n, AM_THREADS, 0, st>>>(n, L->node_off, brp, bcol, bval, act, best);
     MYC_LAUNCHED(ctx);
     am_accept_kernel<<<g_n, AM_THREADS, 0, st>>>(n, best, paired);
     MYC_LAUNCHED(ctx);
     am_root_kernel<<<g_n, AM_THREADS, 0, st>>>(n, L->node_off, brp, bcol, bval, act, paired, root);
     MYC_LAUNCHED(ctx);
-    MYC_CUDA(ctx, cudaMemsetAsync(keep, 0, (size_t)n * sizeof(int32_t), st));
-    am_keep_kernel<<<g_n, AM_THREADS, 0, st>>>(n, L->node_off, brp, bcol, act, nullptr, root, keep);
+    MYC_CUDA(ctx, cudaMemsetAsync(keep, 0, (size_t)(n + 1) * sizeof(int32_t), st));
+    am_keep_kernel<<<g_n, AM_THREADS, 0, st>>>(n, L->node_off, brp, bcol, act, lv == 0 ? act_global : nullptr, root, keep);
     MYC_LAUNCHED(ctx);
     am_lead_kernel<<<g_n, AM_THREADS, 0, st>>>(n, act, root, keep, flag);
     MYC_LAUNCHED(ctx);
@@ -325,7 +516,19 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
     MYC_CUDA(ctx, cudaMemcpyAsync(h_pin, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     MYC_CUDA(ctx, cudaStreamSynchronize(st));
     const int64_t n_c = h_pin[0];
-    if (n_c == 0 || (double)n_c > AMG_MAX_RATIO * (double)n) break;
+    // numbering over the ranks: rank-major, so the coarse level inherits the contiguous partition
+    int64_t c_off[MYC_MAX_WORLD + 1] = {0};
+    int64_t n_c_global = n_c, cnode_off = 0;
+    if (part) {
+      MYC_TRY(myc_dist_allgather_host_i64(ctx, &n_c, 1, h_all, st));
+      for (int q = 0; q < world; ++q) c_off[q + 1] = c_off[q] + h_all[q];
+      n_c_global = c_off[world];
+      cnode_off = c_off[rank];
+    } else {
+      c_off[1] = n_c;
+    }
+    if (n_c_global == 0 || (double)n_c_global > AMG_MAX_RATIO * (double)L->n_global) break;
+    if (n_c_global >= ((int64_t)1 << 30)) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "amg_setup: too many aggregates for 32-bit ids");
     // ---- agg[], member lists
     const size_t items = (size_t)(nb > n ? nb : n) + 1;
     for (int k = 0; k < 2; ++k) {
@@ -345,19 +548,27 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
                                                   (const uint32_t*)ctx->sort_vals[sorted].p, (int32_t*)C->mptr.p,
                                                   (int32_t*)C->mlist.p);
     MYC_LAUNCHED(ctx);
-    // ---- Galerkin operator of the aggregates
-    const int cbits = am_bits_for(n_c + 1);
-    am_coarse_emit_kernel<<<g_n, AM_THREADS, 0, st>>>(n, L->node_off, brp, bcol, act, (const int32_t*)L->agg.p, nullptr,
-                                                      0, (int32_t)n_c, cbits, (uint64_t*)ctx->sort_keys[0].p,
+    // ---- Galerkin operator of the aggregates (columns: GLOBAL aggregate ids)
+    const int32_t* agg_global = nullptr;
+    if (part) {
+      MYC_TRY(myc_ensure(ctx, S->agg_global, (size_t)(L->n_global + 4) * sizeof(int32_t)));
+      am_agg_global_kernel<<<g_n, AM_THREADS, 0, st>>>(n, L->node_off, (const int32_t*)L->agg.p, (int32_t)cnode_off,
+                                                       (int32_t*)S->agg_global.p);
+      MYC_LAUNCHED(ctx);
+      int64_t boff[MYC_MAX_WORLD + 1];
+      for (int q = 0; q <= world; ++q) boff[q] = 4 * lvl_off[q];
+      MYC_TRY(myc_dist_allgatherv(ctx, S->agg_global.p, boff, st));
+      agg_global = (const int32_t*)S->agg_global.p;
+    }
+    const int cbits = am_bits_for(n_c_global + 1);
+    const int rbits = am_bits_for(n_c + 1);
+    am_coarse_emit_kernel<<<g_n, AM_THREADS, 0, st>>>(n, L->node_off, brp, bcol, act, (const int32_t*)L->agg.p, agg_global,
+                                                      cnode_off, (int32_t)n_c, cbits, (uint64_t*)ctx->sort_keys[0].p,
                                                       (uint32_t*)ctx->sort_vals[0].p);
     MYC_LAUNCHED(ctx);
-    MYC_TRY(myc_radix_sort_pairs(ctx, nb, 0, 2 * cbits, &sorted, st));
+    MYC_TRY(myc_radix_sort_pairs(ctx, nb, 0, cbits + rbits, &sorted, st));
     const uint64_t* skeys = (const uint64_t*)ctx->sort_keys[sorted].p;
     const uint32_t* svals = (const uint32_t*)ctx->sort_vals[sorted].p;
-    MYC_TRY(myc_ensure(ctx, S->work[4], (size_t)(nb + 2) * sizeof(int32_t)));
-    MYC_TRY(myc_ensure(ctx, S->work[5], (size_t)(nb + 2) * sizeof(int32_t)));
-    flag = (int32_t*)S->work[4].p;
-    int32_t* uidx = (int32_t*)S->work[5].p;
     const int g_b = grid_for(ctx, ceil_div64(nb, AM_THREADS), 8);
     am_head_kernel<<<g_b, AM_THREADS, 0, st>>>(nb, (int32_t)n_c, cbits, skeys, flag);
     MYC_LAUNCHED(ctx);
@@ -368,10 +579,55 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
     MYC_TRY(myc_ensure(ctx, C->brp, (size_t)(n_c + 2) * sizeof(int32_t)));
     MYC_TRY(myc_ensure(ctx, C->bcol, (size_t)(n_cb + 4) * sizeof(int32_t)));
     MYC_TRY(myc_ensure(ctx, C->bval, (size_t)(n_cb + 4) * 6 * sizeof(double)));
+    if (nb == 0) MYC_CUDA(ctx, cudaMemsetAsync(C->brp.p, 0, (size_t)(n_c + 2) * sizeof(int32_t), st));
     am_coarse_fill_kernel<<<g_b, AM_THREADS, 0, st>>>(nb, (int32_t)n_c, cbits, skeys, svals, flag, uidx, bval, (int32_t)n_cb,
                                                       (int32_t*)C->brp.p, (int32_t*)C->bcol.p, (double*)C->bval.p);
     MYC_LAUNCHED(ctx);
-    C->n = n_c; C->nb = n_cb; C->n_global = n_c; C->node_off = 0;
+    C->n = n_c; C->nb = n_cb; C->n_global = n_c_global; C->node_off = cnode_off;
+    C->replicated = L->replicated ? 2 : 0;
+    C->own_lo = C->own_n = 0; C->agg_shift = 0; C->r_off = -1;
+    L->agg_shift = 0;
+    if (part && n_c_global <= ctx->amg_replicate_nodes) {
+      // ---- the seam: gather the coarse operator onto every rank; from here down everything is redundant
+      int64_t cb_off[MYC_MAX_WORLD + 1] = {0};
+      MYC_TRY(myc_dist_allgather_host_i64(ctx, &n_cb, 1, h_all, st));
+      for (int q = 0; q < world; ++q) cb_off[q + 1] = cb_off[q] + h_all[q];
+      const int64_t nb_g = cb_off[world];
+      if (nb_g >= ((int64_t)1 << 31)) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "amg_setup: replicated level too large");
+      DevBuf f_brp, f_bcol, f_bval;
+      MYC_TRY(myc_ensure(ctx, f_brp, (size_t)(n_c_global + 2) * sizeof(int32_t)));
+      MYC_TRY(myc_ensure(ctx, f_bcol, (size_t)(nb_g + 4) * sizeof(int32_t)));
+      MYC_TRY(myc_ensure(ctx, f_bval, (size_t)(nb_g + 4) * 6 * sizeof(double)));
+      am_brp_section_kernel<<<grid_for(ctx, ceil_div64(n_c, AM_THREADS), 8), AM_THREADS, 0, st>>>(
+          n_c, cnode_off, (const int32_t*)C->brp.p, (int32_t)cb_off[rank], n_c_global, (int32_t)nb_g, (int32_t*)f_brp.p);
+      MYC_LAUNCHED(ctx);
+      if (n_cb > 0) {
+        MYC_CUDA(ctx, cudaMemcpyAsync((int32_t*)f_bcol.p + cb_off[rank], C->bcol.p, (size_t)n_cb * sizeof(int32_t),
+                                      cudaMemcpyDeviceToDevice, st));
+        MYC_CUDA(ctx, cudaMemcpyAsync((double*)f_bval.p + 6 * cb_off[rank], C->bval.p, (size_t)n_cb * 6 * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, st));
+      }
+      int64_t boff[MYC_MAX_WORLD + 1];
+      for (int q = 0; q <= world; ++q) boff[q] = 4 * c_off[q];
+      MYC_TRY(myc_dist_allgatherv(ctx, f_brp.p, boff, st));
+      for (int q = 0; q <= world; ++q) boff[q] = 4 * cb_off[q];
+      MYC_TRY(myc_dist_allgatherv(ctx, f_bcol.p, boff, st));
+      for (int q = 0; q <= world; ++q) boff[q] = 48 * cb_off[q];
+      MYC_TRY(myc_dist_allgatherv(ctx, f_bval.p, boff, st));
+      MYC_CUDA(ctx, cudaStreamSynchronize(st));
+      am_drop(C->brp); am_drop(C->bcol); am_drop(C->bval);
+      C->brp = f_brp; C->bcol = f_bcol; C->bval = f_bval;
+      C->n = n_c_global; C->nb = nb_g; C->node_off = 0;
+      C->replicated = 1; C->own_lo = cnode_off; C->own_n = n_c;
+      // agg[] of the level above indexes the coarse level relative to ITS node_off, which is now 0
+      if (n > 0 && cnode_off > 0) {
+        am_shift_kernel<<<g_n, AM_THREADS, 0, st>>>(n, (int32_t*)L->agg.p, (int32_t)cnode_off);
+        MYC_LAUNCHED(ctx);
+      }
+      L->agg_shift = cnode_off;
+      c_off[0] = 0; c_off[1] = n_c_global;
+    }
+    for (int q = 0; q <= world; ++q) lvl_off[q] = (dist && !C->replicated) ? c_off[q] : (q == 0 ? 0 : C->n);
     brp = (const int32_t*)C->brp.p;
     bcol = (const int32_t*)C->bcol.p;
     bval = (const double*)C->bval.p;
@@ -383,15 +639,26 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   int64_t off = 0;
   for (int l = 0; l < S->n_levels; ++l) {
     AmgLevelHost& H = S->lv[l];
-    if (l > 0) MYC_TRY(myc_ensure(ctx, H.r, (size_t)(3 * H.n + 4) * sizeof(double)));
+    if (l > 0 && H.replicated != 1) MYC_TRY(myc_ensure(ctx, H.r, (size_t)(3 * H.n + 4) * sizeof(double)));
     MYC_TRY(myc_ensure(ctx, H.t, (size_t)(3 * H.n + 4) * sizeof(double)));
     for (int k = 0; k < 2; ++k) {
       H.e_off[k] = off;
       off += (3 * H.n_global + 15) / 16 * 16;
     }
+    H.r_off = -1;
+    if (H.replicated == 1) {                 // the seam level's right-hand side is assembled from every rank's part
+      H.r_off = off;
+      off += (3 * H.n_global + 15) / 16 * 16;
+    }
   }
   S->arena_doubles = off;
-  MYC_TRY(myc_ensure(ctx, S->arena, (size_t)(off + 16) * sizeof(double)));
+  if (dist) {
+    int ok = 1;
+    MYC_TRY(am_peer_ensure(ctx, off + 16, st, &ok));
+    if (!ok) return MYC_OK;                  // no P2P path between some pair of GPUs: collective fallback
+  } else {
+    MYC_TRY(myc_ensure(ctx, S->arena, (size_t)(off + 16) * sizeof(double)));
+  }
   MYC_TRY(myc_ensure(ctx, S->lv_dev, sizeof(AmgLevelDev) * AMG_MAX_LEVELS));
   MYC_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
   MYC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -431,20 +698,28 @@ double myc_amg_bytes_per_iteration(const myc_ctx* ctx) {
   return bytes;
 }
 
-// Introspection for tests and reports: out[0] = owned nodes, out[1] = owned blocks of `level`; out[2] = levels;
-// out[3] = setup time in microseconds.  d_out_agg (may be NULL): the level's aggregate map, n int32.
-extern "C" int myc_amg_level_info(myc_ctx* ctx, int level, int64_t* h_out4, int32_t* d_out_agg, void* stream) {
-  if (!ctx || !h_out4) return MYC_ERR_BAD_ARG;
+// Introspection for tests and reports.  out[0] = nodes and out[1] = blocks of `level` held by this rank, out[2] =
+// levels, out[3] = setup time in microseconds, out[4] = global id of the first held node, out[5] = nodes of the
+// level over all ranks, out[6] = 0 partitioned / 1 first replicated level / 2 replicated, out[7] = what has been
+// added to the level's aggregate map to make it index the next level from that level's first held node.
+// d_out_agg (may be NULL): the level's aggregate map, out[0] int32.
+extern "C" int myc_amg_level_info(myc_ctx* ctx, int level, int64_t* h_out8, int32_t* d_out_agg, void* stream) {
+  if (!ctx || !h_out8) return MYC_ERR_BAD_ARG;
   AmgState* S = ctx->amg;
   if (!S || !S->valid || level < 0 || level >= S->n_levels) MYC_FAIL(ctx, MYC_ERR_STATE, "amg_level_info: no such level");
-  h_out4[0] = S->lv[level].n;
-  h_out4[1] = S->lv[level].nb;
-  h_out4[2] = S->n_levels;
-  h_out4[3] = (int64_t)(S->setup_ms * 1e3);
+  const AmgLevelHost& H = S->lv[level];
+  h_out8[0] = H.n;
+  h_out8[1] = H.nb;
+  h_out8[2] = S->n_levels;
+  h_out8[3] = (int64_t)(S->setup_ms * 1e3);
+  h_out8[4] = H.node_off;
+  h_out8[5] = H.n_global;
+  h_out8[6] = H.replicated;
+  h_out8[7] = H.agg_shift;
   if (d_out_agg) {
     if (level + 1 >= S->n_levels) MYC_FAIL(ctx, MYC_ERR_STATE, "amg_level_info: the coarsest level has no aggregates");
-    MYC_CUDA(ctx, cudaMemcpyAsync(d_out_agg, S->lv[level].agg.p, (size_t)S->lv[level].n * sizeof(int32_t),
-                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    MYC_CUDA(ctx, cudaMemcpyAsync(d_out_agg, H.agg.p, (size_t)H.n * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                  (cudaStream_t)stream));
   }
   return MYC_OK;
 }

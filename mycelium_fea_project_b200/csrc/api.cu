@@ -44,6 +44,8 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
     // way -- so the gate is opt-in
     const char* z = getenv("MYC_HALO_OVERLAP");
     ctx->no_halo_overlap = !(z && z[0] == '1');
+    const char* rn = getenv("MYC_AMG_REPLICATE_NODES");
+    if (rn && rn[0]) ctx->amg_replicate_nodes = atoll(rn);
   }
   e = cudaSetDevice(device_ordinal);
   cudaDeviceProp prop;
@@ -75,7 +77,7 @@ extern "C" int myc_destroy(myc_ctx* ctx) {
   DevBuf* all[] = {&ctx->scan_tmp, &ctx->sort_keys[0], &ctx->sort_keys[1], &ctx->sort_vals[0], &ctx->sort_vals[1],
                    &ctx->sort_table, &ctx->edge_cnt, &ctx->node_deg, &ctx->node_bc, &ctx->partials, &ctx->scalars,
                    &ctx->vec[0], &ctx->vec[1], &ctx->vec[2], &ctx->vec[3], &ctx->vec[4], &ctx->vec[5], &ctx->misc,
-                   &ctx->sym_val, &ctx->sym_col};
+                   &ctx->sym_val, &ctx->sym_col, &ctx->xchg};
   for (DevBuf* b : all) if (b->p) cudaFree(b->p);
   for (DevBuf& b : ctx->lc) if (b.p) cudaFree(b.p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -179,9 +181,21 @@ extern "C" int myc_load_case_host(myc_ctx* ctx, const double* h_coords, const in
   } hint_guard{ctx, ctx->csr_block3};
   ctx->csr_block3 = true;
   MYC_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+  if (n_dof == 0) {                                   // nothing to solve
+    if (h_out_iters) *h_out_iters = 0;
+    if (h_out_relres) *h_out_relres = 0.0;
+    if (h_out_nnz) *h_out_nnz = 0;
+    if (h_out_force) *h_out_force = 0.0;
+    return MYC_OK;
+  }
   MYC_TRY(myc_apply_dirichlet(ctx, n_dof, n_dof, 0, d_rp, d_ci, d_val, d_kd, d_kv, n_known, reg, d_ubc, d_rhs,
                               d_dinv, st));
   double* d_binv = nullptr;
+  if (precond == MYC_PC_AMG) {
+    int levels = 0;
+    MYC_TRY(myc_amg_setup(ctx, n_dof, n_dof, 0, d_rp, d_ci, d_val, d_dinv, reg, &levels, st));
+    if (levels == 0) precond = MYC_PC_BLOCK6;        // hierarchy not applicable to this system (see myc_amg_setup)
+  }
   if (precond == MYC_PC_BLOCK3) {
     MYC_TRY(myc_ensure(ctx, ctx->vec[4], (size_t)(3 * n_dof + 9) * 8));
     d_binv = (double*)ctx->vec[4].p;

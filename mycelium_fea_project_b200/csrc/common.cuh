@@ -51,6 +51,7 @@ struct myc_ctx {
   DevBuf scalars;               // PcgScalars + counters
   DevBuf vec[6];                // PCG work vectors (r, p(global), Ap, ...)
   DevBuf misc;                  // small temporaries (flags, gather-sum output ...)
+  DevBuf xchg;                  // staging of the small host-value all-gathers (dist.cu)
   DevBuf lc[14];                // device copies owned by myc_load_case_host
   DevBuf sym_val, sym_col;      // symmetric 3x3 block view of K for the persistent solver kernels (spmv_sym3.cuh)
   int sym_owner = 0;            // 1: sym_val / sym_col are level 0 of the multigrid hierarchy below
@@ -93,6 +94,13 @@ struct myc_ctx {
   bool peer_ok = false;
   unsigned peer_epoch_red = 0, peer_epoch_halo = 0;
   unsigned amg_epoch_red = 0, amg_epoch_halo = 0;     // the same for the multigrid solver kernel's own flag block
+  // multigrid on several GPUs (amg_setup.cu / pcg_amg.cu): one IPC-shared buffer per rank holding the gathered
+  // correction vectors of all levels followed by the AgPeerSync slots/flags
+  void* amg_peer_own = nullptr;
+  void* amg_peer_base[MYC_MAX_WORLD] = {nullptr};
+  int64_t amg_peer_cap = 0;          // capacity of the vector arena in doubles
+  int64_t amg_replicate_nodes = 65536;   // a level with at most this many nodes over all ranks is held by every rank
+                                         // in full (MYC_AMG_REPLICATE_NODES overrides; tests use small values)
 };
 
 #define MYC_FAIL(ctx, code, ...)                                   \
@@ -174,6 +182,11 @@ int myc_exclusive_scan_i32(myc_ctx* ctx, const int32_t* d_in, int32_t* d_out, in
 // radix_sort.cu: stable LSD sort of (key64, val32) pairs on key bits [start_bit, key_bits).
 // Returns the index (0/1) of the ping-pong buffer holding the result.
 int myc_radix_sort_pairs(myc_ctx* ctx, int64_t n, int start_bit, int key_bits, int* out_buf, cudaStream_t st);
+
+// dist.cu (collective; no-ops / copies on a single rank)
+int myc_dist_allgatherv(myc_ctx* ctx, void* d_buf, const int64_t* h_off_bytes, cudaStream_t st);
+int myc_dist_allgather_host_i64(myc_ctx* ctx, const int64_t* h_mine, int k, int64_t* h_all, cudaStream_t st);
+int myc_dist_allgather_host_64b(myc_ctx* ctx, const void* h_mine64, void* h_all, cudaStream_t st);
 
 // spmv.cu
 int myc_launch_spmv(myc_ctx* ctx, int64_t n_rows, const int32_t* rp, const int32_t* ci,

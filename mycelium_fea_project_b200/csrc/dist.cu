@@ -185,6 +185,51 @@ int myc_dist_allreduce_dev(myc_ctx* ctx, double* d_buf, int n, cudaStream_t st) 
   return MYC_OK;
 }
 
+// All-gather of contiguous, variably sized sections of one device array: rank q owns bytes
+// [h_off_bytes[q], h_off_bytes[q+1]); on return every rank holds all sections (in place).
+int myc_dist_allgatherv(myc_ctx* ctx, void* d_buf, const int64_t* h_off_bytes, cudaStream_t st) {
+  if (ctx->world <= 1) return MYC_OK;
+  NcclApi* a = ctx->nccl;
+  myc_ncclComm_t comm = (myc_ncclComm_t)ctx->comm;
+  char* base = (char*)d_buf;
+  const int64_t my_lo = h_off_bytes[ctx->rank], my_hi = h_off_bytes[ctx->rank + 1];
+  MYC_NCCL(ctx, a->GroupStart());
+  for (int q = 0; q < ctx->world; ++q) {
+    if (q == ctx->rank) continue;
+    const int64_t lo = h_off_bytes[q], hi = h_off_bytes[q + 1];
+    if (my_hi > my_lo) MYC_NCCL(ctx, a->Send(base + my_lo, (size_t)(my_hi - my_lo), MYC_NCCL_UINT8, q, comm, st));
+    if (hi > lo) MYC_NCCL(ctx, a->Recv(base + lo, (size_t)(hi - lo), MYC_NCCL_UINT8, q, comm, st));
+  }
+  MYC_NCCL(ctx, a->GroupEnd());
+  return MYC_OK;
+}
+
+// All-gather of k host int64 per rank (k <= 32): h_all[q * k + j] = value j of rank q.  Synchronises the stream.
+int myc_dist_allgather_host_i64(myc_ctx* ctx, const int64_t* h_mine, int k, int64_t* h_all, cudaStream_t st) {
+  if (k < 1 || k > 32) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "allgather_host: bad count");
+  if (ctx->world <= 1) {
+    memcpy(h_all, h_mine, sizeof(int64_t) * k);
+    return MYC_OK;
+  }
+  MYC_TRY(myc_ensure(ctx, ctx->xchg, (size_t)(ctx->world + 1) * 32 * sizeof(int64_t)));
+  int64_t* d_mine = (int64_t*)ctx->xchg.p;
+  int64_t* d_all = d_mine + 32;
+  MYC_CUDA(ctx, cudaMemcpyAsync(d_mine, h_mine, sizeof(int64_t) * k, cudaMemcpyHostToDevice, st));
+  MYC_NCCL(ctx, ctx->nccl->AllGather(d_mine, d_all, (size_t)k, MYC_NCCL_INT64, (myc_ncclComm_t)ctx->comm, st));
+  MYC_CUDA(ctx, cudaMemcpyAsync(h_all, d_all, sizeof(int64_t) * k * ctx->world, cudaMemcpyDeviceToHost, st));
+  MYC_CUDA(ctx, cudaStreamSynchronize(st));
+  return MYC_OK;
+}
+
+// All-gather of 64 opaque bytes per rank (IPC memory handles).  Synchronises the stream.
+int myc_dist_allgather_host_64b(myc_ctx* ctx, const void* h_mine64, void* h_all, cudaStream_t st) {
+  int64_t mine[8], all[8 * MYC_MAX_WORLD];
+  memcpy(mine, h_mine64, 64);
+  MYC_TRY(myc_dist_allgather_host_i64(ctx, mine, 8, all, st));
+  memcpy(h_all, all, (size_t)64 * ctx->world);
+  return MYC_OK;
+}
+
 extern "C" int myc_halo_exchange(myc_ctx* ctx, double* d_x_global, void* stream) {
   if (!ctx || !d_x_global) return MYC_ERR_BAD_ARG;
   MYC_CUDA(ctx, cudaSetDevice(ctx->device));

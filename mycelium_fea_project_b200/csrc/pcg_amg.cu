@@ -10,10 +10,12 @@
 //   coarsest: AMG_COARSE_SWEEPS - 1 further sweeps  e += omega D^-1 (r - A e)
 //   up   for l = L-2 .. 0:   U1_l: e_l += AMG_SCALE * P e_l+1;   U2_l: e_l += omega D^-1 (r_l - A_l e_l)  (sweep)
 //   CG   w = A_0 u + reg u with gamma = r.u, delta = w.u, r.r folded into the sweep's epilogue -> reduction
-// Every phase ends in a grid barrier.  Phases whose output another GPU gathers (the e vectors read by a sweep)
-// also store the rows a neighbour needs straight into that neighbour's arena (P2P over NVLink) and end in a
-// halo barrier (neighbour flags); restriction and prolongation are rank-local because aggregates never span
-// ranks.  Vector passes deal rows in chunks of 30 per warp (10 whole nodes), the lane of row (node, c) gets its
+// Every phase ends in a grid barrier.  Several GPUs: on a PARTITIONED level, phases whose output another GPU
+// gathers (the e vectors read by a sweep) also store the rows a neighbour needs straight into that neighbour's
+// arena (P2P over NVLink) and end in a halo barrier (neighbour flags); restriction and prolongation are
+// rank-local because aggregates never span ranks.  REPLICATED levels (amg.cuh) are processed by every GPU in
+// full with local barriers only; at the seam every rank restricts onto its own aggregates, stores that part of
+// the right-hand side into every arena, and one all-rank flag exchange completes it.  Vector passes deal rows in chunks of 30 per warp (10 whole nodes), the lane of row (node, c) gets its
 // siblings' values by shuffle and applies row c of the symmetric 3x3 inverse -- the same row-per-lane layout as
 // the sweep's epilogue, so all accesses are coalesced.
 #include "amg.cuh"
@@ -111,9 +113,11 @@ struct AgPut {
     a->arena[a->rank][L.e_off[k] + g] = val;
     bool pushed = false;
     if constexpr (DIST) {
+      if (!L.replicated) {
 #pragma unroll 1
-      for (int q = 0; q < a->world; ++q)
-        if (g >= L.give_lo[q] && g < L.give_hi[q]) { a->arena[q][L.e_off[k] + g] = val; pushed = true; }
+        for (int q = 0; q < a->world; ++q)
+          if (g >= L.give_lo[q] && g < L.give_hi[q]) { a->arena[q][L.e_off[k] + g] = val; pushed = true; }
+      }
     }
     return pushed;
   }
@@ -227,29 +231,35 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
     }
     __syncthreads();
   };
-  // the level's gathered vector is complete everywhere it is read
+  // cross-GPU flag exchange inside a leader barrier: every peer is told that this rank's stores of halo phase e
+  // have been issued (all peers at every phase, so that the epochs stay in step), then the peers in `wait_mask`
+  // are awaited
+  auto flag_barrier = [&](unsigned wait_mask) {
+    ++ep_halo;
+    const unsigned e = ep_halo;
+    const bool block_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
+    pushed = false;
+    leader_barrier(block_pushed, [&](int ln) {
+      if (ln < a.world && ln != a.rank) {
+        __threadfence_system();
+        ag_st_release_sys(&a.sync[ln]->flag_halo[a.rank], e);
+        if ((wait_mask >> ln) & 1u) {
+          unsigned spins = 0;
+          while (ag_ld_acquire_sys(&my_sync->flag_halo[ln]) < e)
+            if (++spins > AG_SPIN_LIMIT) __trap();
+        }
+      }
+    });
+  };
+  // the level's gathered vector is complete everywhere it is read.  The wait covers the neighbours of ALL
+  // partitioned levels (the same ranks on every level for contiguous strips), which also orders this rank's
+  // next stores into a neighbour's vector behind that neighbour's last reads of it.
   auto halo_barrier = [&](const AmgLevelDev& L) {
     if constexpr (!DIST) {
       local_barrier();
     } else {
-      ++ep_halo;
-      const unsigned e = ep_halo;
-      const bool block_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
-      pushed = false;
-      leader_barrier(block_pushed, [&](int ln) {
-        if (ln < a.world && ln != a.rank) {
-          // every neighbour of ANY level is signalled at every halo phase, so that epochs stay in step
-          if ((a.recv_mask_all >> ln) & 1u) {
-            __threadfence_system();
-            ag_st_release_sys(&a.sync[ln]->flag_halo[a.rank], e);
-            if ((L.recv_mask >> ln) & 1u) {
-              unsigned spins = 0;
-              while (ag_ld_acquire_sys(&my_sync->flag_halo[ln]) < e)
-                if (++spins > AG_SPIN_LIMIT) __trap();
-            }
-          }
-        }
-      });
+      if (L.replicated) local_barrier();
+      else flag_barrier(a.recv_mask_all);
     }
   };
 
@@ -293,6 +303,36 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
     EpiAgResidual epi{L.t, L.r, own(L, 0), mask, a.reg};
     tm_sym3_sweep<EpiAgResidual, false, false, true>(pp, 3 * (int64_t)L.n, L.brp, L.bval, L.bcol, arena + L.e_off[0], epi,
                                                      dummy, gw, n_warps, lane, L.nb, TmHaloGate{});
+  };
+  // seam (several GPUs): restriction onto THIS rank's aggregates of the first replicated level, stored into
+  // every rank's copy of the level's right-hand side
+  auto phase_restrict_seam = [&](const AmgLevelDev& Lf, const AmgLevelDev& L) {
+    const int64_t n = 3 * (int64_t)L.own_n;
+    for (int64_t base = gw * 30; base < n; base += n_warps * 30) {
+      const int64_t i = base + lane;
+      if (lane < 30 && i < n) {
+        const int64_t nd = i / 3;
+        const int c = (int)(i - 3 * nd);
+        double sum = 0.0;
+        const int32_t me = L.mptr[nd + 1];
+        for (int32_t m = L.mptr[nd]; m < me; ++m) sum += Lf.t[3 * (int64_t)L.mlist[m] + c];
+        const int64_t g = L.r_off + 3 * (int64_t)L.own_lo + i;
+#pragma unroll 1
+        for (int q = 0; q < a.world; ++q) a.arena[q][g] = sum;
+        pushed = true;
+      }
+    }
+  };
+  // pre-smoothing from zero on a level whose right-hand side is complete: e = omega D^-1 r
+  auto phase_presmooth = [&](const AmgLevelDev& L) {
+    const int64_t n = 3 * (int64_t)L.n;
+    for (int64_t base = gw * 30; base < n; base += n_warps * 30) {
+      const int64_t i = base + lane;
+      const bool ok = lane < 30 && i < n;
+      const double ri = ok ? L.r[i] : 0.0;
+      const double z = ag_dinv_apply(L.dinv, i, ok, ri, lane);
+      if (ok) put(L, 0, i, AMG_OMEGA * z);
+    }
   };
   // D_l (l >= 1): restriction by member lists + pre-smoothing from zero
   auto phase_restrict = [&](const AmgLevelDev& Lf, const AmgLevelDev& L) {
@@ -352,6 +392,15 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
       for (int l = 0; l + 1 < NL; ++l) {
         phase_residual(lv[l], l == 0 ? a.mask0 : nullptr);
         local_barrier();
+        if constexpr (DIST) {
+          if (lv[l + 1].replicated == 1) {
+            phase_restrict_seam(lv[l], lv[l + 1]);
+            flag_barrier((1u << a.world) - 1u);       // every rank's part of r has landed
+            phase_presmooth(lv[l + 1]);
+            local_barrier();
+            continue;
+          }
+        }
         phase_restrict(lv[l], lv[l + 1]);
         halo_barrier(lv[l + 1]);
       }
@@ -469,7 +518,8 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
       S->key_dinv != d_dinv || ctx->sym_owner != 1)
     MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve(MYC_PC_AMG): call myc_amg_setup for this operator and Dirichlet set first");
   const bool dist = ctx->world > 1;
-  if (dist) MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve(MYC_PC_AMG): multi-GPU hierarchy not installed");
+  if (S->world != ctx->world || (dist && (!ctx->amg_peer_own || ctx->amg_peer_cap < S->arena_doubles)))
+    MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve(MYC_PC_AMG): the hierarchy was built for another communicator");
   int coop = 0;
   MYC_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   const size_t smem = tm_sym_smem_bytes(AG_WARPS);
@@ -494,6 +544,7 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
   // ---- level table
   AmgLevelDev h_lv[AMG_MAX_LEVELS];
   memset(h_lv, 0, sizeof(h_lv));
+  unsigned recv_mask_all = 0;
   for (int l = 0; l < S->n_levels; ++l) {
     AmgLevelHost& H = S->lv[l];
     AmgLevelDev& D = h_lv[l];
@@ -508,6 +559,17 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
     D.r = l == 0 ? (double*)ctx->vec[1].p : (double*)H.r.p;
     D.t = (double*)H.t.p;
     D.e_off[0] = H.e_off[0]; D.e_off[1] = H.e_off[1];
+    D.replicated = H.replicated;
+    D.own_lo = (int32_t)H.own_lo; D.own_n = (int32_t)H.own_n;
+    D.r_off = H.r_off;
+    if (H.replicated == 1) D.r = (double*)ctx->amg_peer_own + H.r_off;
+    if (dist && !H.replicated)
+      for (int q = 0; q < ctx->world; ++q) {
+        if (q == ctx->rank) continue;
+        D.give_lo[q] = 3 * H.give_lo[q]; D.give_hi[q] = 3 * H.give_hi[q];
+        if (H.need_hi[q] > H.need_lo[q]) D.recv_mask |= 1u << q;
+      }
+    recv_mask_all |= D.recv_mask;
   }
   MYC_CUDA(ctx, cudaMemcpyAsync(S->lv_dev.p, h_lv, sizeof(AmgLevelDev) * S->n_levels, cudaMemcpyHostToDevice, st));
   MYC_CUDA(ctx, cudaStreamSynchronize(st));      // h_lv is a stack array
@@ -518,7 +580,17 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
   memset(&a, 0, sizeof(a));
   a.lv = (const AmgLevelDev*)S->lv_dev.p;
   a.n_levels = S->n_levels;
-  a.arena[0] = (double*)S->arena.p;
+  if (dist) {
+    for (int q = 0; q < ctx->world; ++q) {
+      a.arena[q] = (double*)ctx->amg_peer_base[q];
+      a.sync[q] = (AgPeerSync*)myc_amg_peer_sync_of(ctx, q);
+    }
+    a.epoch_red0 = ctx->amg_epoch_red;
+    a.epoch_halo0 = ctx->amg_epoch_halo;
+    a.recv_mask_all = recv_mask_all;
+  } else {
+    a.arena[0] = (double*)S->arena.p;
+  }
   a.mask0 = d_dinv;
   a.x = d_x;
   a.w = (double*)ctx->vec[2].p;
@@ -530,14 +602,15 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
   a.bar = bar;
   a.gsum = gsum;
   a.sc = (PcgScalars*)ctx->scalars.p;
-  a.world = 1;
-  a.rank = 0;
+  a.world = ctx->world;
+  a.rank = ctx->rank;
   const int64_t n_tiles = ceil_div64(n_rows / 3, TmCfgSym::NODES);
   int grid = ctx->sm_count;
   if (ceil_div64(n_tiles, AG_WARPS) < grid) grid = (int)ceil_div64(n_tiles, AG_WARPS);
   if (grid < 1) grid = 1;
   void* params[] = {&a};
-  MYC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)pcg_amg_kernel<false>, dim3(grid), dim3(AG_THREADS), params, smem, st));
+  const void* fn = dist ? (const void*)pcg_amg_kernel<true> : (const void*)pcg_amg_kernel<false>;
+  MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(AG_THREADS), params, smem, st));
   ctx->launches++;
   *handled = 1;
   return MYC_OK;

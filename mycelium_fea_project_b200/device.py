@@ -179,12 +179,20 @@ def assemble(ctx: Context, mesh: DeviceMesh, E, A, I, node_range=None) -> Device
 
 
 def apply_dirichlet(ctx: Context, K: DeviceCSR, known_dofs: torch.Tensor, known_vals: torch.Tensor,
-                    reg=REGULARISATION, block3=False, precond=None) -> DirichletSystem:
+                    reg=REGULARISATION, block3=False, precond=None, reuse: DirichletSystem | None = None) -> DirichletSystem:
     """``precond`` ("jacobi", "block3", "block6", "block12", "amg") selects what is built next to the Jacobi
     diagonal: block inverses, or the aggregation-multigrid hierarchy (kept inside the context; it belongs to
     the LAST system prepared with precond="amg").  "amg" needs a node-block-structured, blockwise symmetric K
     and node-complete Dirichlet sets; otherwise the system is prepared for "block6" (``.precond`` tells).
-    ``block3=True`` is the older spelling of precond="block3"."""
+    ``block3=True`` is the older spelling of precond="block3".
+    ``reuse``: a system prepared earlier for the SAME K and the SAME set of known DOFs: only the prescribed
+    values are new, so ubc / rhs are rewritten in place and the preconditioner is kept."""
+    if reuse is not None:
+        _hint(ctx, K)
+        check(ctx.h, lib.myc_apply_dirichlet(ctx.h, K.n_rows, K.n_cols, K.row_offset, _ptr(K.row_ptr), _ptr(K.col_idx),
+                                             _ptr(K.val), _ptr(known_dofs), _ptr(known_vals), known_dofs.shape[0],
+                                             float(reuse.reg), _ptr(reuse.ubc), _ptr(reuse.rhs), _ptr(reuse.dinv), _stream()))
+        return reuse
     if precond is None:
         precond = "block3" if block3 else "jacobi"
     if precond not in _lib.PRECONDITIONERS:
@@ -250,21 +258,28 @@ def pcg(ctx: Context, K: DeviceCSR, sys: DirichletSystem, x0: torch.Tensor | Non
     return x, int(iters.value), float(relres.value)
 
 
-def amg_levels(ctx: Context):
-    """[(nodes, blocks)] per level of the context's current multigrid hierarchy, and its setup time in ms."""
-    out = (C.c_int64 * 4)()
+def amg_levels(ctx: Context, detail=False):
+    """[(nodes, blocks)] per level of the context's current multigrid hierarchy (what THIS rank holds), and its
+    setup time in ms.  ``detail``: dicts with n, nb, node_off, n_global, replicated (0 partitioned over the ranks /
+    single GPU, 1 first replicated level, 2 replicated) and agg_shift instead of the tuples."""
+    out = (C.c_int64 * 8)()
     check(ctx.h, lib.myc_amg_level_info(ctx.h, 0, out, None, _stream()))
     n_levels, setup_ms = int(out[2]), out[3] / 1e3
     levels = []
     for l in range(n_levels):
         check(ctx.h, lib.myc_amg_level_info(ctx.h, l, out, None, _stream()))
-        levels.append((int(out[0]), int(out[1])))
+        if detail:
+            levels.append({"n": int(out[0]), "nb": int(out[1]), "node_off": int(out[4]), "n_global": int(out[5]),
+                           "replicated": int(out[6]), "agg_shift": int(out[7])})
+        else:
+            levels.append((int(out[0]), int(out[1])))
     return levels, setup_ms
 
 
 def amg_aggregates(ctx: Context, level: int) -> torch.Tensor:
-    """node -> aggregate map of ``level`` (int32, -1 = not represented on the next level)."""
-    out = (C.c_int64 * 4)()
+    """node -> aggregate map of ``level`` (int32, -1 = not represented on the next level) for the nodes this rank
+    holds; values index the next level from the first node this rank holds there (see amg_levels(detail=True))."""
+    out = (C.c_int64 * 8)()
     check(ctx.h, lib.myc_amg_level_info(ctx.h, level, out, None, _stream()))
     agg = torch.empty((int(out[0]),), dtype=torch.int32, device=ctx.device)
     check(ctx.h, lib.myc_amg_level_info(ctx.h, level, out, _ptr(agg), _stream()))

@@ -132,9 +132,27 @@ def exchange_halo_torch(x_global, plan: HaloPlan, group=None):
 # ---------------------------------------------------------------------------------------------
 # production path: C library + NCCL
 # ---------------------------------------------------------------------------------------------
+def local_mesh_slice(n1, n2, node_begin, node_end):
+    """What rank [node_begin, node_end) needs of the mesh: the indices of the elements incident to an owned node
+    (in element order, so duplicate elements are summed in the reference's order) and the node range
+    [lo, hi) their end nodes span (owned nodes + the halo the cut elements reach)."""
+    n1 = np.asarray(n1)
+    n2 = np.asarray(n2)
+    m = ((n1 >= node_begin) & (n1 < node_end)) | ((n2 >= node_begin) & (n2 < node_end))
+    idx = np.flatnonzero(m)
+    lo, hi = int(node_begin), int(node_end)
+    if idx.size:
+        lo = min(lo, int(n1[idx].min()), int(n2[idx].min()))
+        hi = max(hi, int(n1[idx].max()) + 1, int(n2[idx].max()) + 1)
+    return idx, lo, hi
+
+
 class DistributedSolver:
-    """Collective driver of one load case on a row-partitioned mesh.  Every rank holds the whole
-    (small) mesh description; matrices and solver vectors are partitioned."""
+    """Collective driver of one load case on a row-partitioned mesh.  The constructor sees the whole mesh
+    description on the host (it is what a snapshot reader hands over), but each rank uploads and keeps only its
+    share: the elements incident to its nodes and the coordinates of its nodes + halo; matrices and solver
+    vectors are partitioned (src/fea_petsc_parallel.cpp:236 -- without its every-rank-assembles-everything loop,
+    :242-265)."""
 
     def __init__(self, mesh_host, active=None, device=None):
         import torch
@@ -154,7 +172,18 @@ class DistributedSolver:
         # cuts on even nodes, so that the aligned 6x6 Jacobi blocks stay rank-local ("block6" on N > 1 GPUs)
         self.block6 = True
         self.plan = make_plan(n1, n2, active, self.n_nodes, self.rank, self.world, all_gather, align=2)
-        self.mesh = dv.DeviceMesh.from_host(coords, n1, n2, active, device=self.ctx.device)
+        # this rank's share of the mesh.  Node ids stay global (the assembler indexes coords with them), so the
+        # coordinate array keeps its global length on the device, but only [coord_lo, coord_hi) is ever written or read.
+        self.elem_index, self.coord_lo, self.coord_hi = local_mesh_slice(n1, n2, self.plan.node_begin, self.plan.node_end)
+        n1h, n2h = np.asarray(n1), np.asarray(n2)
+        if n1h.size and (min(n1h.min(), n2h.min()) < 0 or max(n1h.max(), n2h.max()) >= self.n_nodes):
+            raise IndexError("element end node outside [0, n_nodes)")
+        dev = self.ctx.device
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+        coords_d = torch.empty((self.n_nodes, 3), dtype=torch.float64, device=dev)
+        coords_d[self.coord_lo:self.coord_hi] = up(np.asarray(coords, dtype=np.float64).reshape(-1, 3)[self.coord_lo:self.coord_hi], np.float64)
+        act = np.ones(len(self.elem_index), np.uint8) if active is None else np.asarray(active)[self.elem_index].astype(np.uint8)
+        self.mesh = dv.DeviceMesh(coords_d, up(n1h[self.elem_index], np.int32), up(n2h[self.elem_index], np.int32), up(act, np.uint8))
         if self.world > 1 and self.ctx.world == 1:
             path = nccl_library_path().encode()
             uid = np.zeros(128, dtype=np.uint8)
@@ -224,9 +253,12 @@ class DistributedSolver:
         self._install_plan()
         return dv.true_residual(self.ctx, K, system, x)
 
-    def load_case(self, K, known_dofs, known_vals, react_dofs=None, rtol=1e-10, precond="block3",
-                  maxit=500_000, reg=1e-12, gather_U=True):
-        """Returns dict(U (global, on every rank if gather_U), iterations, relres, total_force)."""
+    def load_case(self, K, known_dofs, known_vals, react_dofs=None, rtol=1e-10, precond="amg",
+                  maxit=500_000, reg=1e-12, gather_U=True, system=None):
+        """Returns dict(U (global, on every rank if gather_U), iterations, relres, total_force).
+        ``precond``: "amg" (aggregation multigrid, built collectively; prepared as "block6" where the hierarchy is
+        not applicable), "block6", "block3" or "jacobi".  ``system``: reuse the Dirichlet system (and its
+        preconditioner) of an earlier call for the same K and known DOFs -- only the prescribed values are new."""
         import torch
         from . import device as dv
         from ._lib import lib, check
@@ -239,15 +271,22 @@ class DistributedSolver:
             # the 12-row groups would need cuts on multiples of 4 nodes: a row-partitioned solve uses the
             # 3x3 node blocks instead
             precond = "block3"
-        sysd = dv.apply_dirichlet(ctx, K, kd, kv, reg, precond=precond)
-        self._ensure_peer(K.n_cols)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        sysd = dv.apply_dirichlet(ctx, K, kd, kv, reg, precond=precond, reuse=system)
+        precond = sysd.precond
+        if precond != "amg":
+            self._ensure_peer(K.n_cols)
+        ev[1].record()
         x, iters, relres = dv.pcg(ctx, K, sysd, precond=precond, rtol=rtol, maxit=maxit)
         U = dv.merge_solution(ctx, K, sysd, x)         # own rows of a zeroed global vector
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         total_force = None
-        if gather_U or react_dofs is not None:
-            if self.world > 1:
+        if self.world > 1:
+            if gather_U:
                 check(ctx.h, lib.myc_allgather_owned(ctx.h, C.c_void_p(U.data_ptr()), stream))
+            elif react_dofs is not None:               # K @ U on the own rows only needs the neighbours' boundary values
+                check(ctx.h, lib.myc_halo_exchange(ctx.h, C.c_void_p(U.data_ptr()), stream))
         if react_dofs is not None:
             rd = np.asarray(react_dofs, dtype=np.int64)
             lo, hi = K.row_offset, K.row_offset + K.n_rows
@@ -257,4 +296,7 @@ class DistributedSolver:
             buf = (C.c_double * 1)(part)
             check(ctx.h, lib.myc_allreduce_sum(ctx.h, buf, 1, stream))
             total_force = float(buf[0])
-        return {"U": U, "x": x, "system": sysd, "iterations": iters, "relres": relres, "total_force": total_force}
+        ev[2].record()
+        ev[2].synchronize()
+        return {"U": U, "x": x, "system": sysd, "iterations": iters, "relres": relres, "total_force": total_force,
+                "precond": precond, "ms_setup": ev[0].elapsed_time(ev[1]), "ms_solve": ev[1].elapsed_time(ev[2])}

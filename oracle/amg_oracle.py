@@ -35,6 +35,8 @@ COARSE_SWEEPS = 8
 MIN_NODES = 200        # a level with at most this many nodes is the coarsest
 MAX_LEVELS = 16
 MAX_RATIO = 0.8        # stop if a level does not shrink below MAX_RATIO * n
+REPLICATE_NODES = 16384  # multi-GPU: a level with at most this many nodes (over all ranks) is held by every rank
+                         # in full, so from there on aggregates are formed without regard to the row partition
 
 
 class Level:
@@ -85,6 +87,9 @@ def aggregate(L):
     w = -((L.bval[:, 0] + L.bval[:, 3]) + L.bval[:, 5])
     off = (cols != rows) & L.act[rows] & L.act[cols]
     cand = off & (w > 0)
+    owner = getattr(L, "owner", None)
+    if owner is not None:                     # row-partitioned hierarchy: aggregates never span ranks
+        cand &= owner[rows] == owner[cols]
     best = _strongest(rows[cand], cols[cand], w[cand], n)                       # propose
     idx = np.arange(n)
     paired = np.where((best >= 0) & (best[np.maximum(best, 0)] == idx), best, -1)   # accept
@@ -128,6 +133,11 @@ def coarsen(L, agg, n_c):
     C.bval = vals
     C.act = np.ones(n_c, bool)
     C.reg = L.reg
+    owner = getattr(L, "owner", None)
+    if owner is not None and n_c > REPLICATE_NODES:   # an aggregate lives on the rank of its members
+        C.owner = np.zeros(n_c, dtype=owner.dtype)
+        m = agg >= 0
+        C.owner[agg[m]] = owner[m]
     return C
 
 
@@ -217,12 +227,16 @@ def vcycle(levels, l, r):
     return e + OMEGA * apply_dinv(L, r - L.A @ e)
 
 
-def amg_pcg(K, free_mask, b, rtol=1e-10, maxit=5000, reg=1e-12, verbose=False):
+def amg_pcg(K, free_mask, b, rtol=1e-10, maxit=5000, reg=1e-12, verbose=False, node_offsets=None):
     """PCG on A = K restricted to the free DOFs + reg I (rows/cols of known DOFs are zero, x = 0 there)
-    with the V-cycle as M^-1.  Returns (x, iterations, levels)."""
+    with the V-cycle as M^-1.  Returns (x, iterations, levels).
+    ``node_offsets`` (world+1,): the row partition of a multi-GPU solve -- rank r owns nodes
+    [node_offsets[r], node_offsets[r+1]) and aggregates are formed inside a rank only."""
     L0 = level_from_csr(K, free_mask, reg)
     if L0 is None:
         raise ValueError("AMG needs node-complete Dirichlet sets")
+    if node_offsets is not None:
+        L0.owner = (np.searchsorted(np.asarray(node_offsets), np.arange(L0.n), side="right") - 1).astype(np.int32)
     levels = build_hierarchy(L0, verbose)
     A = levels[0].A
     fm = np.asarray(free_mask, bool)

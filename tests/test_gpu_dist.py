@@ -21,10 +21,11 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, N, precond, ret, no_peer=False, shape=None, case="Y"):
+def _worker(rank, world, port, N, precond, ret, no_peer=False, shape=None, case="Y", env=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     if no_peer:
         os.environ["MYC_NO_PEER"] = "1"
+    os.environ.update(env or {})
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -59,14 +60,33 @@ def _worker(rank, world, port, N, precond, ret, no_peer=False, shape=None, case=
         U2o = fo.solve_system(Ko, kd2, kv2)
         err2 = np.linalg.norm(out2["U"].cpu().numpy() - U2o) / np.linalg.norm(U2o)
         assert err2 <= 1e-8, err2
-        ret[rank] = (out["iterations"], err, out["total_force"], bool(getattr(solver.ctx, "peer_enabled", False)))
+        extra = None
+        if precond == "amg":
+            assert out["system"].precond == "amg", "the multigrid hierarchy was not built"
+            levels, _ = dv.amg_levels(solver.ctx, detail=True)
+            extra = [(l["n_global"], l["replicated"]) for l in levels]
+            if rank == 0:
+                # the numpy restatement with the same row partition and replication threshold: same level sizes,
+                # same iteration count (it runs the standard recurrence, the GPU the single-reduction form)
+                from oracle import amg_oracle as ao
+                ao.REPLICATE_NODES = int(os.environ.get("MYC_AMG_REPLICATE_NODES", ao.REPLICATE_NODES))
+                free = np.ones(Ko.shape[0], bool)
+                free[kd] = False
+                ubc = np.zeros(Ko.shape[0])
+                ubc[kd] = kv
+                b = -(Ko @ ubc)
+                b[kd] = 0.0
+                _, it_ref, lv_ref = ao.amg_pcg(Ko, free, b, rtol=1e-12, node_offsets=solver.plan.offsets)
+                assert [l[0] for l in extra] == [l.n for l in lv_ref], (extra, [l.n for l in lv_ref])
+                assert abs(out["iterations"] - it_ref) <= max(2, it_ref // 20), (out["iterations"], it_ref)
+        ret[rank] = (out["iterations"], err, out["total_force"], bool(getattr(solver.ctx, "peer_enabled", False)), extra)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("precond,no_peer", [("jacobi", False), ("jacobi", True), ("block3", False)])
 def test_two_gpu_solve_matches_oracle(precond, no_peer):
-    """no_peer False: fused persistent kernel over NVLink peer memory (jacobi and block3); True: NCCL loop."""
+    """no_peer False: persistent solver kernel over NVLink peer memory (jacobi and block3); True: NCCL loop."""
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
@@ -102,3 +122,39 @@ def test_four_gpu_strips(case, no_peer):
     mp.spawn(_worker, args=(world, _free_port(), 0, "jacobi", ret, no_peer, shape, case), nprocs=world, join=True)
     assert len(ret) == world
     assert len({v[0] for v in ret.values()}) == 1 and len({v[2] for v in ret.values()}) == 1
+
+
+@pytest.mark.parametrize("replicate_nodes", [0, 300, 65536])
+def test_two_gpu_amg(replicate_nodes):
+    """Aggregation-multigrid PCG on a row-partitioned mesh: partitioned levels exchange their correction vectors
+    through NVLink peer memory, levels at or below the replication threshold are processed by every rank in
+    full.  0: every level partitioned; 300: two partitioned coarse levels, then the seam; 65536 (default): the
+    first coarse level is already replicated.  Same parity bars as every solver (U vs the direct solve <= 1e-8),
+    level sizes and iteration count equal to the numpy restatement with the same partition."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), 128, "amg", ret, False, None, "Y",
+                            {"MYC_AMG_REPLICATE_NODES": str(replicate_nodes)}), nprocs=world, join=True)
+    assert len(ret) == world
+    assert ret[0][0] == ret[1][0] and ret[0][2] == ret[1][2]
+    assert ret[0][4] == ret[1][4]                       # same hierarchy shape on both ranks
+    kinds = [k for _, k in ret[0][4]]
+    if replicate_nodes == 0:
+        assert set(kinds) == {0}
+    else:
+        assert kinds[0] == 0 and 1 in kinds and kinds[-1] in (1, 2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs >= 4 CUDA devices")
+@pytest.mark.parametrize("case,replicate_nodes", [("X", 300), ("Y", 300), ("Y", 65536)])
+def test_four_gpu_amg(case, replicate_nodes):
+    world = 4
+    shape = (4 * 48, 64) if case == "X" else (64, 4 * 48)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), 0, "amg", ret, False, shape, case,
+                            {"MYC_AMG_REPLICATE_NODES": str(replicate_nodes)}), nprocs=world, join=True)
+    assert len(ret) == world
+    assert len({v[0] for v in ret.values()}) == 1 and len({v[2] for v in ret.values()}) == 1
+    assert len({tuple(v[4]) for v in ret.values()}) == 1

@@ -583,8 +583,7 @@ def test_ramp_letter_fixtures(name, golden_dir, tmp_path, monkeypatch):
         shutil.copyfile(os.path.join(src, f), tmp_path / f)
     for k, v in GOLDEN_CONSTS[name].items():
         monkeypatch.setattr(fs, k, v)
-    monkeypatch.setattr(fs, "PCG_RTOL", 1e-13)
-    fs.fea_solver(str(tmp_path), tol=fs.GRIP_LENGTH)
+    fs.fea_solver(str(tmp_path), tol=fs.GRIP_LENGTH)        # shipped defaults: PCG_RTOL, PCG_PRECOND, warm start, incremental
     rd = lambda base, f: pd.read_csv(os.path.join(base, "fea_results", f), float_precision="round_trip")
     for f in ("active_elements.csv",):
         a, b = rd(tmp_path, f), rd(src, f)
@@ -597,25 +596,59 @@ def test_ramp_letter_fixtures(name, golden_dir, tmp_path, monkeypatch):
     assert os.path.isfile(tmp_path / "fea_results" / "runtime.txt")
 
 
-def test_ramp_real_snapshot_cascade(golden_dir, monkeypatch):
-    """results/sim_20251117_181147 (7,375 nodes, 25 disconnected components, duplicate elements) with
-    the COMMITTED constants through the GPU ramp: the 40-step failure cascade must equal the
-    reference's committed active_elements.csv, the force-displacement curve must agree to 1e-7."""
+def _real_snapshot(golden_dir):
     d = os.path.join(golden_dir, "ref_results", "sim_20251117_181147")
     nodes = pd.read_csv(io.BytesIO(gzip.open(os.path.join(d, "nodes.csv.gz")).read()))
     elems = pd.read_csv(io.BytesIO(gzip.open(os.path.join(d, "elements.csv.gz")).read()))
-    monkeypatch.setattr(fs, "PCG_RTOL", 1e-12)
-    rec = fs.fea_ramp(nodes[["x", "y", "z"]].values, elems["n1"].values, elems["n2"].values)
     g = np.load(os.path.join(d, "fea_results", "active_elements.npz"))
     gold = np.unpackbits(g["packed"], axis=1)[:, :int(g["n_elems"])].astype(bool)
+    fd = pd.read_csv(os.path.join(d, "fea_results", "force_displacement.csv"), float_precision="round_trip").values
+    return nodes[["x", "y", "z"]].values, elems["n1"].values, elems["n2"].values, gold, fd
+
+
+@pytest.mark.parametrize("precond", ["amg", "block6"])
+def test_ramp_real_snapshot_cascade(golden_dir, monkeypatch, precond):
+    """results/sim_20251117_181147 (7,375 nodes, 25 disconnected components, duplicate elements) with
+    the COMMITTED constants through the GPU ramp AS SHIPPED (default PCG_RTOL, warm start, incremental
+    re-assembly): the 40-step failure cascade must equal the reference's committed active_elements.csv,
+    the force-displacement curve must agree to 1e-7."""
+    coords, n1, n2, gold, fd = _real_snapshot(golden_dir)
+    monkeypatch.setattr(fs, "PCG_PRECOND", precond)
+    rec = fs.fea_ramp(coords, n1, n2)
     mine = np.array(rec["active"])
     assert mine.shape == gold.shape
     assert np.array_equal(mine, gold), f"cascade differs at steps {np.nonzero((mine != gold).any(1))[0][:5]}"
-    fd = pd.read_csv(os.path.join(d, "fea_results", "force_displacement.csv"), float_precision="round_trip").values
     got = np.array(rec["force_disp"])
     assert np.array_equal(got[:, 0], fd[:, 0])
     assert np.abs(got[:, 1] - fd[:, 1]).max() <= 1e-7 * np.abs(fd[:, 1]).max()
     print("real snapshot ramp: iterations per step", rec["iterations"][:6], "...")
+
+
+def test_ramp_warm_start_and_incremental_switches(golden_dir):
+    """The ramp's two shortcuts -- warm start from the scaled previous solution, and reuse of K / the Dirichlet
+    system / the preconditioner while no element fails -- change neither the failure cascade nor (to 1e-8)
+    the records, at the default tolerance.  K is re-assembled exactly on step 0 and after every failure."""
+    coords, n1, n2, gold, fd = _real_snapshot(golden_dir)
+    base = fs.fea_ramp(coords, n1, n2)
+    act = np.array(base["active"])
+    assert np.array_equal(act, gold)
+    n_act = act.sum(1)
+    before = np.concatenate([[len(n1)], n_act[:-1]])           # active elements when step k starts
+    failed_in_step = n_act != before
+    expect = [True] + [bool(f) for f in failed_in_step[:-1]]     # step k re-assembles iff step k-1 lost elements
+    assert base["reassembled"] == expect, "re-assembly must follow topology changes only"
+    assert not all(base["reassembled"]) and any(i == 0 for i in base["iterations"][1:]), "no step took a shortcut"
+    for kw in (dict(warm_start=False), dict(incremental=False), dict(warm_start=False, incremental=False)):
+        rec = fs.fea_ramp(coords, n1, n2, **kw)
+        assert np.array_equal(np.array(rec["active"]), gold), kw
+        a, b = np.array(rec["force_disp"]), np.array(base["force_disp"])
+        assert np.abs(a - b).max() <= 1e-8 * np.abs(b).max(), kw
+        da, db = np.array(rec["disp"]), np.array(base["disp"])
+        assert np.abs(da - db).max() <= 1e-8 * np.abs(db).max(), kw
+        sa, sb = np.array(rec["stress"]), np.array(base["stress"])
+        assert np.abs(sa - sb).max() <= 1e-8 * np.abs(sb).max(), kw
+        if not kw.get("incremental", True):
+            assert all(rec["reassembled"])
 
 
 @pytest.mark.parametrize("case", ["X", "shear"])
