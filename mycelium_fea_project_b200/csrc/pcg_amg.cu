@@ -53,6 +53,7 @@ struct AmgArgs {
   int world, rank;
   unsigned epoch_red0, epoch_halo0;
   unsigned recv_mask_all;                 // peers this rank gathers from on any level
+  unsigned long long* timing;             // -DMYC_AMG_TIMING: ns per phase slot, accumulated by block 0 ([4 l + phase], [64] = CG)
 };
 
 __device__ __forceinline__ unsigned ag_ld_acquire_gpu(const unsigned* p) {
@@ -201,6 +202,19 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   TmSymPipe pp;
   tm_sym_pipe_init(pp, ag_smem, AG_WARPS, warp, lane);
 
+#ifdef MYC_AMG_TIMING
+  unsigned long long t_last = 0;
+  auto tick = [&](int slot) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (slot >= 0) a.timing[slot] += t - t_last;
+      t_last = t;
+    }
+  };
+#else
+  auto tick = [](int) {};
+#endif
   // ---- barriers
   auto local_barrier = [&]() { ag_grid_barrier(&a.bar[0], epoch); };
   // arrive / leader / release with cross-GPU work done by warp 0 of the last-arriving block
@@ -380,9 +394,11 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   bool first = true;
   for (;;) {
     // ---- u = M^-1 r : V-cycle, its first phase fused with the CG recurrences
+    tick(-1);
     phase_d0(first, alpha, beta);
     first = false;
     halo_barrier(L0);
+    tick(0);
     if (NL == 1) {
       for (int k = 1; k < AMG_COARSE_SWEEPS; ++k) {
         phase_smooth(lv[0], (k - 1) & 1, k & 1, a.mask0, true);
@@ -392,27 +408,33 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
       for (int l = 0; l + 1 < NL; ++l) {
         phase_residual(lv[l], l == 0 ? a.mask0 : nullptr);
         local_barrier();
+        tick(4 * l + 1);
         if constexpr (DIST) {
           if (lv[l + 1].replicated == 1) {
             phase_restrict_seam(lv[l], lv[l + 1]);
             flag_barrier((1u << a.world) - 1u);       // every rank's part of r has landed
             phase_presmooth(lv[l + 1]);
             local_barrier();
+            tick(4 * (l + 1));
             continue;
           }
         }
         phase_restrict(lv[l], lv[l + 1]);
         halo_barrier(lv[l + 1]);
+        tick(4 * (l + 1));
       }
       for (int k = 1; k < AMG_COARSE_SWEEPS; ++k) {
         phase_smooth(lv[NL - 1], (k - 1) & 1, k & 1, nullptr, true);
         halo_barrier(lv[NL - 1]);
       }
+      tick(4 * (NL - 1) + 1);
       for (int l = NL - 2; l >= 0; --l) {
         phase_prolong(lv[l], lv[l + 1], fin(l + 1));
         halo_barrier(lv[l]);
+        tick(4 * l + 2);
         phase_smooth(lv[l], 0, 1, l == 0 ? a.mask0 : nullptr, l == 0);
         if (l == 0) halo_barrier(L0); else local_barrier();
+        tick(4 * l + 3);
       }
     }
     // ---- w = A u, partial dots
@@ -481,6 +503,7 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
       if (threadIdx.x < 3) s_tot[threadIdx.x] = __ldcg(&a.gsum[par * 4 + threadIdx.x]);
     }
     __syncthreads();
+    tick(64);
     const double gamma = s_tot[0], delta = s_tot[1];
     rr = s_tot[2];
     if (!isfinite(rr)) { status = 2; break; }
@@ -604,6 +627,11 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
   a.sc = (PcgScalars*)ctx->scalars.p;
   a.world = ctx->world;
   a.rank = ctx->rank;
+#ifdef MYC_AMG_TIMING
+  MYC_TRY(myc_ensure(ctx, ctx->xchg, 4096));
+  a.timing = (unsigned long long*)ctx->xchg.p;
+  MYC_CUDA(ctx, cudaMemsetAsync(a.timing, 0, 72 * sizeof(unsigned long long), st));
+#endif
   const int64_t n_tiles = ceil_div64(n_rows / 3, TmCfgSym::NODES);
   int grid = ctx->sm_count;
   if (ceil_div64(n_tiles, AG_WARPS) < grid) grid = (int)ceil_div64(n_tiles, AG_WARPS);
@@ -613,5 +641,17 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
   MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(AG_THREADS), params, smem, st));
   ctx->launches++;
   *handled = 1;
+#ifdef MYC_AMG_TIMING
+  {
+    unsigned long long h[72];
+    MYC_CUDA(ctx, cudaMemcpyAsync(h, a.timing, sizeof(h), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaStreamSynchronize(st));
+    fprintf(stderr, "[amg timing, block 0, us summed over the solve] level: presmooth/restrict  residual(|coarsest sweeps)  prolong  postsmooth\n");
+    for (int l = 0; l < S->n_levels; ++l)
+      fprintf(stderr, "  L%-2d n=%-9lld %10.1f %10.1f %10.1f %10.1f\n", l, (long long)S->lv[l].n, h[4 * l] / 1e3, h[4 * l + 1] / 1e3,
+              h[4 * l + 2] / 1e3, h[4 * l + 3] / 1e3);
+    fprintf(stderr, "  CG sweep + reduction %10.1f\n", h[64] / 1e3);
+  }
+#endif
   return MYC_OK;
 }
