@@ -42,6 +42,7 @@ struct AmgLevelDev {                     // what the solver kernel reads (device
   const int32_t* brp;                    // [n+1]
   const int32_t* bcol;                   // [nb]   3 * global node id
   const double* bval;                    // [nb*6]
+  const float* bval32;                   // [nb*6]  the same rounded to FP32: what the V-cycle's sweeps stream (null: FP64)
   const double* dinv;                    // [n*6]
   const int32_t* agg;                    // [n]    aggregate (local index on the next level) or -1; null on the coarsest
   const int32_t* mptr;                   // [n+1]  members on the previous level; null on level 0
@@ -57,6 +58,7 @@ struct AmgLevelDev {                     // what the solver kernel reads (device
                                          // (the seam: r is assembled from every rank's part); 2: replicated, deeper
   int32_t own_lo, own_n;                 // seam level: the aggregates of THIS rank (global ids own_lo .. own_lo+own_n);
                                          // mptr / mlist describe exactly those
+  int32_t l2_keep;                       // the level's operator is small enough to stay in L2 between iterations
   int64_t r_off;                         // seam level: offset of r inside every rank's arena (r then points there)
 };
 
@@ -67,6 +69,7 @@ struct AmgLevelHost {
   int64_t agg_shift = 0;                 // what was added to this level's agg[] so that it indexes level l+1 relative
                                          // to that level's node_off (non-zero only above the seam)
   DevBuf brp, bcol, bval, dinv, agg, mptr, mlist, r, t;
+  DevBuf bval32;                         // FP32 copy of the level's block values (level 0: of the context's sym_val)
   int64_t e_off[2] = {0, 0};
   int64_t r_off = -1;                    // seam level: r lives in the arena
   int64_t need_lo[MYC_MAX_WORLD] = {0}, need_hi[MYC_MAX_WORLD] = {0};     // node ranges (global, this level)
@@ -88,6 +91,7 @@ struct AmgState {
   DevBuf act_global;                     // several GPUs: level 0 activity of every node (global ids)
   DevBuf agg_global;                     // several GPUs: global aggregate id of every node of the level being coarsened
   int world = 1;                         // ranks the hierarchy was built for
+  bool f32 = true;                       // the V-cycle streams FP32 copies of the level operators (MYC_AMG_FP64=1: no)
   DevBuf work[6];                        // best / paired / root / keep / flags / scan output (int32 x n)
   DevBuf arena;                          // single GPU: the gathered correction vectors of all levels
   int64_t arena_doubles = 0;             // doubles the e vectors of all levels need

@@ -273,6 +273,13 @@ am_halo_range_kernel(int64_t nb, const int32_t* __restrict__ bcol, AmOffsets o, 
   }
 }
 
+// FP32 copy of a level's block values for the V-cycle's sweeps (amg_sweep.cuh)
+__global__ void __launch_bounds__(AM_THREADS)
+am_to_f32_kernel(int64_t n, const double* __restrict__ in, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (float)in[i];
+}
+
 int am_bits_for(int64_t n) {
   int b = 1;
   while (((int64_t)1 << b) < n) ++b;
@@ -358,7 +365,7 @@ int myc_amg_destroy(myc_ctx* ctx) {
   if (!s) return MYC_OK;
   for (AmgLevelHost& L : s->lv) {
     am_drop(L.brp); am_drop(L.bcol); am_drop(L.bval); am_drop(L.dinv); am_drop(L.agg); am_drop(L.mptr); am_drop(L.mlist);
-    am_drop(L.r); am_drop(L.t);
+    am_drop(L.r); am_drop(L.t); am_drop(L.bval32);
   }
   am_drop(s->lv_dev); am_drop(s->brp0); am_drop(s->arena); am_drop(s->act0); am_drop(s->act_global); am_drop(s->agg_global);
   for (DevBuf& b : s->work) am_drop(b);
@@ -635,6 +642,18 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
     ++lv;
   }
   S->n_levels = lv + 1;
+  // ---- FP32 copies of the level operators for the V-cycle's sweeps
+  S->f32 = !ctx->amg_fp64;
+  if (S->f32)
+    for (int l = 0; l < S->n_levels; ++l) {
+      AmgLevelHost& H = S->lv[l];
+      const double* src = l == 0 ? (const double*)ctx->sym_val.p : (const double*)H.bval.p;
+      MYC_TRY(myc_ensure(ctx, H.bval32, (size_t)(H.nb + 4) * 6 * sizeof(float)));
+      if (H.nb > 0) {
+        am_to_f32_kernel<<<grid_for(ctx, ceil_div64(6 * H.nb, AM_THREADS), 8), AM_THREADS, 0, st>>>(6 * H.nb, src, (float*)H.bval32.p);
+        MYC_LAUNCHED(ctx);
+      }
+    }
   // ---- vectors: r, t per level (level 0's r is the CG residual); arena of the gathered correction vectors
   int64_t off = 0;
   for (int l = 0; l < S->n_levels; ++l) {

@@ -44,6 +44,8 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
     // way -- so the gate is opt-in
     const char* z = getenv("MYC_HALO_OVERLAP");
     ctx->no_halo_overlap = !(z && z[0] == '1');
+    const char* f64 = getenv("MYC_AMG_FP64");
+    ctx->amg_fp64 = f64 && f64[0] == '1';
     const char* rn = getenv("MYC_AMG_REPLICATE_NODES");
     if (rn && rn[0]) ctx->amg_replicate_nodes = atoll(rn);
   }

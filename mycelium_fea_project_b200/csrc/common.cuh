@@ -99,6 +99,7 @@ struct myc_ctx {
   void* amg_peer_own = nullptr;
   void* amg_peer_base[MYC_MAX_WORLD] = {nullptr};
   int64_t amg_peer_cap = 0;          // capacity of the vector arena in doubles
+  bool amg_fp64 = false;             // MYC_AMG_FP64=1: the V-cycle streams the FP64 level operators (default: FP32 copies)
   int64_t amg_replicate_nodes = 65536;   // a level with at most this many nodes over all ranks is held by every rank
                                          // in full (MYC_AMG_REPLICATE_NODES overrides; tests use small values)
 };

@@ -19,11 +19,14 @@
 // siblings' values by shuffle and applies row c of the symmetric 3x3 inverse -- the same row-per-lane layout as
 // the sweep's epilogue, so all accesses are coalesced.
 #include "amg.cuh"
-#include "spmv_sym3.cuh"
+#include "amg_sweep.cuh"
 
 namespace {
 
-constexpr int AG_WARPS = 32;
+#ifndef AG_WARPS_N
+#define AG_WARPS_N 32
+#endif
+constexpr int AG_WARPS = AG_WARPS_N;
 constexpr int AG_THREADS = 32 * AG_WARPS;
 constexpr unsigned AG_SPIN_LIMIT = 1u << 28;
 static_assert(AMG_COARSE_SWEEPS >= 2 && AMG_COARSE_SWEEPS % 2 == 0, "the coarsest level's result must land in buffer 1");
@@ -92,17 +95,27 @@ __device__ __forceinline__ void ag_grid_barrier(unsigned* bar, unsigned& epoch) 
 
 // z = (D^-1 v)_row for the row-per-lane layout: lanes 3q, 3q+1, 3q+2 (< 30) hold the rows of one node.
 // All 32 lanes call; `ok` lanes get their row of the symmetric inverse (xx xy xz yy yz zz) applied.
-__device__ __forceinline__ double ag_dinv_apply(const double* __restrict__ dinv, int64_t row, bool ok, double v, int lane) {
+// The row of the inverse is loaded separately (AgDinvRow, early: its latency then hides behind the rest of the
+// phase) from the shuffle + multiply (ag_dinv_mul, when the residual is known).
+struct AgDinvRow { double m0, m1, m2; };
+__device__ __forceinline__ AgDinvRow ag_dinv_row(const double* __restrict__ dinv, int64_t row, bool ok, int lane) {
+  if (!ok) return AgDinvRow{0.0, 0.0, 0.0};
+  const int c = lane % 3;
+  const double* d = dinv + 6 * (row / 3);
+  // row c of [[d0 d1 d2] [d1 d3 d4] [d2 d4 d5]]
+  return AgDinvRow{d[c], d[c == 0 ? 1 : c + 2], d[c + 2 + (c > 0)]};
+}
+__device__ __forceinline__ double ag_dinv_mul(const AgDinvRow& m, double v, int lane) {
   const int c = lane % 3;
   const int src = lane < 30 ? lane - c : 0;
   const double v0 = __shfl_sync(0xffffffffu, v, src);
   const double v1 = __shfl_sync(0xffffffffu, v, src + 1);
   const double v2 = __shfl_sync(0xffffffffu, v, src + 2);
-  if (!ok) return 0.0;
-  const double* d = dinv + 6 * (row / 3);
-  // row c of [[d0 d1 d2] [d1 d3 d4] [d2 d4 d5]]
-  const double m0 = d[c], m1 = d[c == 0 ? 1 : c + 2], m2 = d[c + 2 + (c > 0)];
-  return m0 * v0 + m1 * v1 + m2 * v2;
+  return m.m0 * v0 + m.m1 * v1 + m.m2 * v2;
+}
+__device__ __forceinline__ double ag_dinv_apply(const double* __restrict__ dinv, int64_t row, bool ok, double v, int lane) {
+  const AgDinvRow m = ag_dinv_row(dinv, row, ok, lane);
+  return ag_dinv_mul(m, v, lane);
 }
 
 // stores one row of a gathered correction vector: own arena, plus every peer that gathers that row
@@ -152,11 +165,13 @@ struct EpiAgSmooth {        // e_out = e + omega D^-1 (r - (A e + reg e))
   double reg;
   AgPut<DIST> put;
   bool* pushed;
-  struct Pre { double ri, ei, mi; };
-  __device__ __forceinline__ Pre load(int64_t i) const { return Pre{r[i], e_own[i], mask ? mask[i] : 1.0}; }
+  struct Pre { double ri, ei, mi; AgDinvRow m; };
+  __device__ __forceinline__ Pre load(int64_t i) const {      // called by the lanes that own a row (lane = i % 30 + ...)
+    return Pre{r[i], e_own[i], mask ? mask[i] : 1.0, ag_dinv_row(L->dinv, i, true, (int)(i % 3))};
+  }
   __device__ __forceinline__ void row_warp(int64_t i, bool ok, double sum, const Pre& pre, double (&)[1], int lane) const {
     const double res = (ok && pre.mi != 0.0) ? pre.ri - (sum + reg * pre.ei) : 0.0;
-    const double z = ag_dinv_apply(L->dinv, i, ok, res, lane);
+    const double z = ag_dinv_mul(pre.m, res, lane);
     if (ok) {
       const double val = pre.ei + AMG_OMEGA * z;
       if (push) { if (put(*L, k_out, i, val)) *pushed = true; }
@@ -182,15 +197,18 @@ struct EpiAgCg {            // w = A u + reg u ; acc = {r.u, w.u, r.r}
   }
 };
 
-template <bool DIST>
+// F32: the sweeps inside the V-cycle stream the FP32 copies of the level operators (amg_sweep.cuh); the CG sweep
+// w = A u always streams the FP64 operator.
+template <bool DIST, bool F32>
 __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   extern __shared__ __align__(128) unsigned char ag_smem[];
   __shared__ double s_red[AG_WARPS][3];
   __shared__ double s_tot[3];
   __shared__ int s_leader;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t gw = (int64_t)warp * gridDim.x + blockIdx.x;       // block-fastest: small levels spread over all SMs
-  const int64_t n_warps = (int64_t)gridDim.x * AG_WARPS;
+  // 32-bit row / tile arithmetic throughout (a rank holds < 2^31 rows): the kernel runs at the 64-register limit
+  const int gw = warp * (int)gridDim.x + (int)blockIdx.x;          // block-fastest: small levels spread over all SMs
+  const int n_warps = (int)gridDim.x * AG_WARPS;
   const AmgLevelDev* const lv = a.lv;
   const int NL = a.n_levels;
   double* const arena = a.arena[a.rank];
@@ -199,8 +217,13 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   unsigned epoch = 0, ep_red = a.epoch_red0, ep_halo = a.epoch_halo0;
   bool pushed = false;                  // this thread stored into a peer since the last halo barrier
   const AgPut<DIST> put{&a};
-  TmSymPipe pp;
-  tm_sym_pipe_init(pp, ag_smem, AG_WARPS, warp, lane);
+  AgPipe pp;
+  ag_pipe_init(pp, ag_smem, AG_WARPS, warp, lane);
+  using PcVal = typename std::conditional<F32, float, double>::type;       // value type of the V-cycle's operators
+  constexpr int PcStages = F32 ? AG_STAGES_F32 : AG_STAGES_F64;
+  auto pc_val = [](const AmgLevelDev& L) -> const PcVal* {
+    if constexpr (F32) return L.bval32; else return L.bval;
+  };
 
 #ifdef MYC_AMG_TIMING
   unsigned long long t_last = 0;
@@ -279,7 +302,7 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
 
   // ---- phases
   const AmgLevelDev L0 = lv[0];
-  const int64_t n0 = 3 * (int64_t)L0.n;
+  const int n0 = 3 * L0.n;
   double* const r0 = L0.r;
   auto own = [&](const AmgLevelDev& L, int k) -> double* { return arena + L.e_off[k] + 3 * (int64_t)L.node_off; };
   const int fin_coarsest = (AMG_COARSE_SWEEPS - 1) & 1;
@@ -288,26 +311,29 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   // D0: CG recurrences (or their initialisation) + pre-smoothing of level 0
   auto phase_d0 = [&](bool first, double alpha, double beta) {
     const double* u = own(L0, 1);
-    for (int64_t base = gw * 30; base < n0; base += n_warps * 30) {
-      const int64_t i = base + lane;
+    for (int base = gw * 30; base < n0; base += n_warps * 30) {
+      const int i = base + lane;
       const bool ok = lane < 30 && i < n0;
       double ri = 0.0;
+      // every load of the row is issued before the first store (the arrays may alias as far as the compiler knows)
+      const AgDinvRow m = ag_dinv_row(L0.dinv, i, ok, lane);
       if (ok) {
         if (first) {
+          ri = r0[i];
           a.p[i] = 0.0;
           a.s[i] = 0.0;
-          ri = r0[i];
         } else {
-          const double pi = u[i] + beta * a.p[i];
-          const double si = a.w[i] + beta * a.s[i];
+          const double ui = u[i], pi0 = a.p[i], wi = a.w[i], si0 = a.s[i], xi = a.x[i], rr0 = r0[i], mk = a.mask0[i];
+          const double pi = ui + beta * pi0;
+          const double si = wi + beta * si0;
+          ri = mk != 0.0 ? rr0 - alpha * si : 0.0;
           a.p[i] = pi;
           a.s[i] = si;
-          a.x[i] += alpha * pi;
-          ri = a.mask0[i] != 0.0 ? r0[i] - alpha * si : 0.0;
+          a.x[i] = xi + alpha * pi;
           r0[i] = ri;
         }
       }
-      const double z = ag_dinv_apply(L0.dinv, i, ok, ri, lane);
+      const double z = ag_dinv_mul(m, ri, lane);
       if (ok && put(L0, 0, i, AMG_OMEGA * z)) pushed = true;
     }
   };
@@ -315,17 +341,17 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   auto phase_residual = [&](const AmgLevelDev& L, const double* mask) {
     double dummy[1] = {0.0};
     EpiAgResidual epi{L.t, L.r, own(L, 0), mask, a.reg};
-    tm_sym3_sweep<EpiAgResidual, false, false, true>(pp, 3 * (int64_t)L.n, L.brp, L.bval, L.bcol, arena + L.e_off[0], epi,
-                                                     dummy, gw, n_warps, lane, L.nb, TmHaloGate{});
+    ag_sweep<EpiAgResidual, PcVal, PcStages>(pp, 3 * (int64_t)L.n, L.brp, pc_val(L), L.bcol, arena + L.e_off[0], epi, dummy,
+                                             gw, n_warps, lane, L.nb, L.l2_keep != 0);
   };
   // seam (several GPUs): restriction onto THIS rank's aggregates of the first replicated level, stored into
   // every rank's copy of the level's right-hand side
   auto phase_restrict_seam = [&](const AmgLevelDev& Lf, const AmgLevelDev& L) {
-    const int64_t n = 3 * (int64_t)L.own_n;
-    for (int64_t base = gw * 30; base < n; base += n_warps * 30) {
-      const int64_t i = base + lane;
+    const int n = 3 * L.own_n;
+    for (int base = gw * 30; base < n; base += n_warps * 30) {
+      const int i = base + lane;
       if (lane < 30 && i < n) {
-        const int64_t nd = i / 3;
+        const int nd = i / 3;
         const int c = (int)(i - 3 * nd);
         double sum = 0.0;
         const int32_t me = L.mptr[nd + 1];
@@ -339,9 +365,9 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   };
   // pre-smoothing from zero on a level whose right-hand side is complete: e = omega D^-1 r
   auto phase_presmooth = [&](const AmgLevelDev& L) {
-    const int64_t n = 3 * (int64_t)L.n;
-    for (int64_t base = gw * 30; base < n; base += n_warps * 30) {
-      const int64_t i = base + lane;
+    const int n = 3 * L.n;
+    for (int base = gw * 30; base < n; base += n_warps * 30) {
+      const int i = base + lane;
       const bool ok = lane < 30 && i < n;
       const double ri = ok ? L.r[i] : 0.0;
       const double z = ag_dinv_apply(L.dinv, i, ok, ri, lane);
@@ -350,19 +376,26 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   };
   // D_l (l >= 1): restriction by member lists + pre-smoothing from zero
   auto phase_restrict = [&](const AmgLevelDev& Lf, const AmgLevelDev& L) {
-    const int64_t n = 3 * (int64_t)L.n;
-    for (int64_t base = gw * 30; base < n; base += n_warps * 30) {
-      const int64_t i = base + lane;
+    const int n = 3 * L.n;
+    for (int base = gw * 30; base < n; base += n_warps * 30) {
+      const int i = base + lane;
       const bool ok = lane < 30 && i < n;
       double sum = 0.0;
+      const AgDinvRow dm = ag_dinv_row(L.dinv, i, ok, lane);
       if (ok) {
-        const int64_t nd = i / 3;
-        const int c = (int)(i - 3 * nd);
-        const int32_t me = L.mptr[nd + 1];
-        for (int32_t m = L.mptr[nd]; m < me; ++m) sum += Lf.t[3 * (int64_t)L.mlist[m] + c];
+        const int nd = i / 3;
+        const int c = i - 3 * nd;
+        const int32_t mb = L.mptr[nd], me = L.mptr[nd + 1];
+        // aggregates have 2..4 members as a rule: fetch the first four lists entries / values together
+        const int32_t k0 = mb < me ? L.mlist[mb] : 0, k1 = mb + 1 < me ? L.mlist[mb + 1] : 0;
+        const int32_t k2 = mb + 2 < me ? L.mlist[mb + 2] : 0, k3 = mb + 3 < me ? L.mlist[mb + 3] : 0;
+        const double t0 = mb < me ? Lf.t[3 * (int64_t)k0 + c] : 0.0, t1 = mb + 1 < me ? Lf.t[3 * (int64_t)k1 + c] : 0.0;
+        const double t2 = mb + 2 < me ? Lf.t[3 * (int64_t)k2 + c] : 0.0, t3 = mb + 3 < me ? Lf.t[3 * (int64_t)k3 + c] : 0.0;
+        sum = ((t0 + t1) + t2) + t3;                         // member order, like the loop below
+        for (int32_t m = mb + 4; m < me; ++m) sum += Lf.t[3 * (int64_t)L.mlist[m] + c];
         L.r[i] = sum;
       }
-      const double z = ag_dinv_apply(L.dinv, i, ok, sum, lane);
+      const double z = ag_dinv_mul(dm, sum, lane);
       if (ok && put(L, 0, i, AMG_OMEGA * z)) pushed = true;
     }
   };
@@ -370,21 +403,25 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   auto phase_smooth = [&](const AmgLevelDev& L, int k_in, int k_out, const double* mask, bool push) {
     double dummy[1] = {0.0};
     EpiAgSmooth<DIST> epi{&L, k_out, push, L.r, own(L, k_in), mask, a.reg, put, &pushed};
-    tm_sym3_sweep<EpiAgSmooth<DIST>, false, false, true>(pp, 3 * (int64_t)L.n, L.brp, L.bval, L.bcol, arena + L.e_off[k_in],
-                                                         epi, dummy, gw, n_warps, lane, L.nb, TmHaloGate{});
+    ag_sweep<EpiAgSmooth<DIST>, PcVal, PcStages>(pp, 3 * (int64_t)L.n, L.brp, pc_val(L), L.bcol, arena + L.e_off[k_in], epi,
+                                                 dummy, gw, n_warps, lane, L.nb, L.l2_keep != 0);
   };
   // U1_l: e_l += SCALE * P e_l+1
   auto phase_prolong = [&](const AmgLevelDev& L, const AmgLevelDev& Lc, int kc) {
-    const int64_t n = 3 * (int64_t)L.n;
+    const int n = 3 * L.n;
     const double* e = own(L, 0);
     const double* ec = own(Lc, kc);
-    for (int64_t base = gw * 30; base < n; base += n_warps * 30) {
-      const int64_t i = base + lane;
-      if (lane < 30 && i < n) {
-        const int64_t nd = i / 3;
-        const int32_t ag = L.agg[nd];
-        if (ag >= 0 && put(L, 0, i, e[i] + AMG_SCALE * ec[3 * (int64_t)ag + (i - 3 * nd)])) pushed = true;
-      }
+    const int stride = n_warps * 30;
+    for (int base = gw * 30; base < n; base += 2 * stride) {          // two chunks per round: twice the loads in flight
+      const int i0 = base + lane, i1 = i0 + stride;
+      const bool ok0 = lane < 30 && i0 < n, ok1 = lane < 30 && i1 < n;
+      const int nd0 = i0 / 3, nd1 = i1 / 3;
+      const int32_t ag0 = ok0 ? L.agg[nd0] : -1, ag1 = ok1 ? L.agg[nd1] : -1;
+      const double e0 = ag0 >= 0 ? e[i0] : 0.0, e1 = ag1 >= 0 ? e[i1] : 0.0;
+      const double c0 = ag0 >= 0 ? ec[3 * (int64_t)ag0 + (i0 - 3 * nd0)] : 0.0;
+      const double c1 = ag1 >= 0 ? ec[3 * (int64_t)ag1 + (i1 - 3 * nd1)] : 0.0;
+      if (ag0 >= 0 && put(L, 0, i0, e0 + AMG_SCALE * c0)) pushed = true;
+      if (ag1 >= 0 && put(L, 0, i1, e1 + AMG_SCALE * c1)) pushed = true;
     }
   };
 
@@ -441,8 +478,8 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
     double acc[3] = {0.0, 0.0, 0.0};
     {
       EpiAgCg epi{a.w, own(L0, 1), r0, a.reg};
-      tm_sym3_sweep<EpiAgCg, false, false, true>(pp, n0, L0.brp, L0.bval, L0.bcol, arena + L0.e_off[1], epi, acc, gw,
-                                                 n_warps, lane, L0.nb, TmHaloGate{});
+      ag_sweep<EpiAgCg, double, AG_STAGES_F64>(pp, n0, L0.brp, L0.bval, L0.bcol, arena + L0.e_off[1], epi, acc, gw, n_warps,
+                                               lane, L0.nb, L0.l2_keep != 0);
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -545,10 +582,12 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
     MYC_FAIL(ctx, MYC_ERR_STATE, "pcg_solve(MYC_PC_AMG): the hierarchy was built for another communicator");
   int coop = 0;
   MYC_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-  const size_t smem = tm_sym_smem_bytes(AG_WARPS);
+  const size_t smem = ag_smem_bytes(AG_WARPS);
+  const bool f32 = S->f32;
   if (ctx->amg_max_blocks_per_sm < 0) {
     int mn = 1 << 30;
-    const void* fns[2] = {(const void*)pcg_amg_kernel<false>, (const void*)pcg_amg_kernel<true>};
+    const void* fns[4] = {(const void*)pcg_amg_kernel<false, false>, (const void*)pcg_amg_kernel<true, false>,
+                          (const void*)pcg_amg_kernel<false, true>, (const void*)pcg_amg_kernel<true, true>};
     for (const void* fn : fns) {
       int b = 0;
       MYC_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -568,6 +607,18 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
   AmgLevelDev h_lv[AMG_MAX_LEVELS];
   memset(h_lv, 0, sizeof(h_lv));
   unsigned recv_mask_all = 0;
+  // small levels stay in L2 across iterations (126 MB): evict-last for them, evict-first for the big streams.
+  // Counted from the coarsest level up: a level's operator <= 16 MB, 48 MB in total.
+  bool l2_keep[AMG_MAX_LEVELS] = {false};
+  {
+    double total = 0.0;
+    for (int l = S->n_levels - 1; l >= 0; --l) {
+      const double need = (double)S->lv[l].nb * 52.0;
+      if (need > 16e6 || total + need > 48e6) break;
+      total += need;
+      l2_keep[l] = true;
+    }
+  }
   for (int l = 0; l < S->n_levels; ++l) {
     AmgLevelHost& H = S->lv[l];
     AmgLevelDev& D = h_lv[l];
@@ -575,6 +626,7 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
     D.brp = l == 0 ? (const int32_t*)S->brp0.p : (const int32_t*)H.brp.p;
     D.bcol = l == 0 ? (const int32_t*)ctx->sym_col.p : (const int32_t*)H.bcol.p;
     D.bval = l == 0 ? (const double*)ctx->sym_val.p : (const double*)H.bval.p;
+    D.bval32 = f32 ? (const float*)H.bval32.p : nullptr;
     D.dinv = (const double*)H.dinv.p;
     D.agg = l + 1 < S->n_levels ? (const int32_t*)H.agg.p : nullptr;
     D.mptr = l > 0 ? (const int32_t*)H.mptr.p : nullptr;
@@ -582,6 +634,7 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
     D.r = l == 0 ? (double*)ctx->vec[1].p : (double*)H.r.p;
     D.t = (double*)H.t.p;
     D.e_off[0] = H.e_off[0]; D.e_off[1] = H.e_off[1];
+    D.l2_keep = l2_keep[l] ? 1 : 0;
     D.replicated = H.replicated;
     D.own_lo = (int32_t)H.own_lo; D.own_n = (int32_t)H.own_n;
     D.r_off = H.r_off;
@@ -637,7 +690,8 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
   if (ceil_div64(n_tiles, AG_WARPS) < grid) grid = (int)ceil_div64(n_tiles, AG_WARPS);
   if (grid < 1) grid = 1;
   void* params[] = {&a};
-  const void* fn = dist ? (const void*)pcg_amg_kernel<true> : (const void*)pcg_amg_kernel<false>;
+  const void* fn = dist ? (f32 ? (const void*)pcg_amg_kernel<true, true> : (const void*)pcg_amg_kernel<true, false>)
+                        : (f32 ? (const void*)pcg_amg_kernel<false, true> : (const void*)pcg_amg_kernel<false, false>);
   MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(AG_THREADS), params, smem, st));
   ctx->launches++;
   *handled = 1;

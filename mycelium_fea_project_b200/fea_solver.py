@@ -204,15 +204,22 @@ def analyze_load_case(mesh: dv.DeviceMesh, known_dofs, known_vals, react_dofs=No
 # the driver (fea_solver.py:186-335)
 # ---------------------------------------------------------------------------------------------
 def load_snapshot(results_dir):
-    """(coords, n1, n2) from nodes.csv / elements.csv (fea_solver.py:193-196); a ``mesh.npz``
-    side-car, if present, is preferred (CSV parsing dominates at >= 2048^2)."""
-    side = os.path.join(results_dir, "mesh.npz")
-    if os.path.isfile(side):
-        z = np.load(side)
-        return z["coords"], z["n1"], z["n2"]
+    """nodes.csv / elements.csv of a results/sim_* directory (fea_solver.py:193-196) -> (coords, n1, n2).
+    A ``mesh.npz`` side-car (snapshot_io / synth.write_snapshot) is preferred when it is at least as new as both
+    CSVs (or when there are no CSVs); a side-car older than an edited CSV is ignored.
+    The reference addresses grip nodes by the ``node_id`` column (:209-210) and elements by row position of the
+    node table (:82-83); both agree only if node_id == row index, which is checked here."""
     import pandas as pd
-    nodes = pd.read_csv(os.path.join(results_dir, "nodes.csv"))
-    elems = pd.read_csv(os.path.join(results_dir, "elements.csv"))
+    npz = os.path.join(results_dir, "mesh.npz")
+    csvs = [os.path.join(results_dir, f) for f in ("nodes.csv", "elements.csv")]
+    have_csv = all(os.path.isfile(c) for c in csvs)
+    if os.path.isfile(npz) and (not have_csv or os.path.getmtime(npz) >= max(os.path.getmtime(c) for c in csvs)):
+        m = np.load(npz)
+        return m["coords"], m["n1"], m["n2"]
+    nodes = pd.read_csv(csvs[0])
+    elems = pd.read_csv(csvs[1])
+    if "node_id" in nodes.columns and not np.array_equal(nodes["node_id"].values, np.arange(len(nodes))):
+        raise ValueError(f"{csvs[0]}: node_id must equal the row index (the reference mixes both addressings)")
     return nodes[["x", "y", "z"]].values, elems["n1"].values, elems["n2"].values
 
 
@@ -227,7 +234,8 @@ def fea_ramp(coords, n1, n2, tol=None, load_case="Y", warm_start=True, verbose=F
     mesh = dv.DeviceMesh.from_host(coords, n1, n2)
     hi, lo = grip_nodes(coords, tol, axis)
     react = _dev(3 * hi + comp, np.int64)
-    rec = {"stress": [], "active": [], "disp": [], "force_disp": [], "iterations": [], "reassembled": []}
+    rec = {"stress": [], "active": [], "disp": [], "force_disp": [], "iterations": [], "reassembled": [],
+           "solve_seconds": []}
     x_prev, step_prev, topology_changed = None, 0, False
     K_prev = sys_prev = None
     for step in range(N_STEPS):
@@ -248,12 +256,16 @@ def fea_ramp(coords, n1, n2, tol=None, load_case="Y", warm_start=True, verbose=F
         # hierarchy / block inverses) are unchanged -- only the prescribed values move -- so neither the assembly
         # nor the preconditioner setup is redone (the reference re-assembles every step, :220).
         reuse = incremental and K_prev is not None and not topology_changed
+        t_solve = time.time()
         try:
             res = analyze_load_case(mesh, known_dofs, known_vals, react_dofs=react, x0=x0,
                                     K=K_prev if reuse else None, system=sys_prev if reuse else None)
         except MyceliumFeaError as exc:              # the reference's LinAlgError branch (:250-254)
             print(f"Solver failure at step {step + 1}: {exc}. Saving partial results and stopping.")
             break
+        # what the reference's solve_runtime.txt times (:247-261: solve_system + K @ U); here it also covers the
+        # (re-)assembly and preconditioner setup of the step, which run inside the same call
+        rec["solve_seconds"].append(time.time() - t_solve)
         rec["reassembled"].append(not reuse)
         K_prev, sys_prev = res.K, res.system
         x_prev, step_prev = res.x, step
@@ -313,6 +325,10 @@ def fea_solver(results_dir, tol=None, load_case="Y", binary_outputs=None):
                             force_disp=np.array(rec["force_disp"]))
     else:
         write_results(fea_dir, rec, len(n1))
+    with open(os.path.join(fea_dir, "solve_runtime.txt"), "w") as f:          # fea_solver.py:214-215, 260-261
+        f.write("step, runtime_s\n")
+        for k, t in enumerate(rec["solve_seconds"]):
+            f.write(f"{k + 1}, {t:.6f}\n")
     total = time.time() - start
     with open(os.path.join(fea_dir, "runtime.txt"), "w") as f:
         f.write(f"Total FEA runtime: {total:.6f} seconds\n")

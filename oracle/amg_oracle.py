@@ -35,7 +35,9 @@ COARSE_SWEEPS = 8
 MIN_NODES = 200        # a level with at most this many nodes is the coarsest
 MAX_LEVELS = 16
 MAX_RATIO = 0.8        # stop if a level does not shrink below MAX_RATIO * n
-REPLICATE_NODES = 16384  # multi-GPU: a level with at most this many nodes (over all ranks) is held by every rank
+PC_FP32 = True         # the V-cycle's level operators are stored rounded to FP32 (csrc/amg_sweep.cuh); products and sums
+                       # stay FP64, the CG operator stays FP64.  False restates MYC_AMG_FP64=1.
+REPLICATE_NODES = 65536  # multi-GPU: a level with at most this many nodes (over all ranks) is held by every rank
                          # in full, so from there on aggregates are formed without regard to the row partition
 
 
@@ -167,6 +169,7 @@ def build_hierarchy(L0, verbose=False):
         L = levels[-1]
         L.dinv = diag_inverse(L)
         L.A = to_scipy(L)
+        L.A_pc = to_scipy(L, PC_FP32)
         if len(levels) >= MAX_LEVELS or L.n <= MIN_NODES:
             break
         agg, n_c = aggregate(L)
@@ -179,9 +182,10 @@ def build_hierarchy(L0, verbose=False):
     return levels
 
 
-def to_scipy(L):
-    """scalar CSR of the level operator restricted to active nodes, + reg I on active nodes"""
-    v = L.bval
+def to_scipy(L, f32=False):
+    """scalar CSR of the level operator restricted to active nodes, + reg I on active nodes.
+    f32: block values rounded to FP32 first (what the V-cycle's sweeps stream on the GPU)."""
+    v = L.bval.astype(np.float32).astype(np.float64) if f32 else L.bval
     data = np.stack([v[:, 0], v[:, 1], v[:, 2], v[:, 1], v[:, 3], v[:, 4], v[:, 2], v[:, 4], v[:, 5]], axis=1).reshape(-1, 3, 3)
     m = L.act[_rows(L)] & L.act[L.bnode]
     data = data * m[:, None, None]
@@ -219,12 +223,12 @@ def vcycle(levels, l, r):
     e = OMEGA * apply_dinv(L, r)
     if l == len(levels) - 1:
         for _ in range(COARSE_SWEEPS - 1):
-            e = e + OMEGA * apply_dinv(L, r - L.A @ e)
+            e = e + OMEGA * apply_dinv(L, r - L.A_pc @ e)
         return e
-    t = r - L.A @ e
+    t = r - L.A_pc @ e
     ec = vcycle(levels, l + 1, restrict(L, t))
     e = e + SCALE * prolong(L, ec)
-    return e + OMEGA * apply_dinv(L, r - L.A @ e)
+    return e + OMEGA * apply_dinv(L, r - L.A_pc @ e)
 
 
 def amg_pcg(K, free_mask, b, rtol=1e-10, maxit=5000, reg=1e-12, verbose=False, node_offsets=None):

@@ -166,3 +166,63 @@ def test_halo_exchange_and_partitioned_pcg_gloo(world):
     assert len(ret) == world
     its = {v[0] for v in ret.values()}
     assert len(its) == 1          # every rank took the same number of iterations
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_local_mesh_slice_is_what_a_rank_assembles_from(world):
+    """The per-rank share of the mesh (DistributedSolver uploads only this): assembling a rank's rows from its
+    incident elements alone gives the verbatim row slice of the global K, and the coordinate range covers every
+    end node of those elements."""
+    coords, n1, n2 = synth_network(24, 40, seed=5)
+    active = np.ones(len(n1), bool)
+    K = fo.assemble_global_stiffness(coords, n1, n2, active)
+    off = md.partition_nodes(len(coords), world, align=2)
+    seen = np.zeros(len(n1), int)
+    for r in range(world):
+        idx, lo, hi = md.local_mesh_slice(n1, n2, off[r], off[r + 1])
+        seen[idx] += 1
+        assert np.all(np.diff(idx) > 0)                                  # element order kept
+        assert lo <= off[r] and hi >= off[r + 1]
+        assert min(n1[idx].min(), n2[idx].min()) >= lo and max(n1[idx].max(), n2[idx].max()) < hi
+        c = np.full_like(coords, np.nan)
+        c[lo:hi] = coords[lo:hi]                                         # nothing outside the range may be read
+        Kr = fo.assemble_global_stiffness(c, n1[idx], n2[idx], np.ones(len(idx), bool))[3 * off[r]:3 * off[r + 1]]
+        ref = K[3 * off[r]:3 * off[r + 1]]
+        assert np.array_equal(Kr.indptr, ref.indptr) and np.array_equal(Kr.indices, ref.indices)
+        assert np.array_equal(Kr.data, ref.data)
+    assert seen.min() >= 1 and seen.max() <= 2                           # cut elements live on both sides
+
+
+@pytest.mark.parametrize("world,replicate", [(1, 0), (2, 0), (4, 0), (4, 500), (3, 10 ** 9)])
+def test_partitioned_multigrid_restatement_solves_the_system(world, replicate, monkeypatch):
+    """oracle/amg_oracle.py with a row partition (aggregates confined to a rank above the replication threshold,
+    unrestricted below it) is still a symmetric positive preconditioner: PCG reaches the direct solve, in a number
+    of iterations close to the unpartitioned hierarchy's.  (The GPU tests compare the CUDA path with this.)"""
+    from oracle import amg_oracle as ao
+    monkeypatch.setattr(ao, "REPLICATE_NODES", replicate)
+    coords, n1, n2 = synth_network(64, seed=0)
+    K = fo.assemble_global_stiffness(coords, n1, n2, np.ones(len(n1), bool))
+    hi, lo = fo.grip_nodes(coords, 0.5)
+    kd, kv = fo.build_bc(hi, lo, 0.02, -0.02)
+    free = np.ones(K.shape[0], bool)
+    free[kd] = False
+    ubc = np.zeros(K.shape[0])
+    ubc[kd] = kv
+    b = -(K @ ubc)
+    b[kd] = 0.0
+    off = md.partition_nodes(len(coords), world, 2) if world > 1 else None
+    x, it, levels = ao.amg_pcg(K, free, b, rtol=1e-12, node_offsets=off)
+    x0, it0, levels0 = ao.amg_pcg(K, free, b, rtol=1e-12)
+    U = x + ubc
+    Uo = fo.solve_system(K, kd, kv)
+    assert np.linalg.norm(U - Uo) <= 1e-8 * np.linalg.norm(Uo)
+    assert it <= 2 * it0 + 5
+    for l in levels[:-1]:                                   # aggregates never span ranks while the level is partitioned
+        own = getattr(l, "owner", None)
+        if own is not None:
+            m = l.agg >= 0
+            first = np.full(l.n_coarse, -1)
+            first[l.agg[m][::-1]] = own[m][::-1]
+            assert np.array_equal(first[l.agg[m]], own[m])
+    if world > 1 and replicate >= 10 ** 9:
+        assert not hasattr(levels[1], "owner")              # replicated from the first coarse level on

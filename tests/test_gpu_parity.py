@@ -685,7 +685,7 @@ def test_snapshot_cli_with_binary_sidecar(tmp_path, monkeypatch):
     r1 = fs.fea_solver(str(d1), tol=fs.GRIP_LENGTH)
     r2 = fs.fea_solver(str(d2), tol=fs.GRIP_LENGTH)
     for f in ("stress_record.csv", "active_elements.csv", "node_displacements.csv", "force_displacement.csv",
-              "runtime.txt"):
+              "runtime.txt", "solve_runtime.txt"):
         assert os.path.isfile(d1 / "fea_results" / f) and os.path.isfile(d2 / "fea_results" / f)
     # the CSV path parses coordinates like the reference (pandas default parser, <= 1 ulp off)
     a, b = np.array(r1["disp"]), np.array(r2["disp"])

@@ -53,3 +53,27 @@ def test_converter_roundtrips_reference_snapshot(golden_dir, tmp_path):
     assert list(nodes1.columns) == list(nodes0.columns) and list(elems1.columns) == list(elems0.columns)
     assert np.abs(nodes1[["x", "y", "z"]].values - nodes0[["x", "y", "z"]].values).max() <= 1e-15
     assert elems1.equals(elems0)
+
+
+def test_stale_sidecar_is_ignored_and_node_ids_are_checked(tmp_path):
+    """An edited CSV wins over an older mesh.npz; a node table whose node_id is not the row index is rejected
+    (the reference addresses grips by node_id and elements by row position, src/fea_solver.py:82-83, 209-210)."""
+    import os
+    import pandas as pd
+    import pytest
+    from mycelium_fea_project_b200 import fea_solver as fs
+    coords, n1, n2 = synth_network(12, 9, seed=2)
+    d = str(tmp_path / "s")
+    write_snapshot(d, coords, n1, n2, binary_sidecar=True)
+    nodes = pd.read_csv(os.path.join(d, "nodes.csv"))
+    nodes["x"] += 1.0
+    nodes.to_csv(os.path.join(d, "nodes.csv"), index=False)
+    t = os.path.getmtime(os.path.join(d, "mesh.npz"))
+    os.utime(os.path.join(d, "nodes.csv"), (t + 5, t + 5))              # the CSV is now newer than the side-car
+    c, _, _ = fs.load_snapshot(d)
+    assert np.abs(c[:, 0] - (coords[:, 0] + 1.0)).max() <= 1e-12
+    nodes["node_id"] = nodes["node_id"].values[::-1].copy()
+    nodes.to_csv(os.path.join(d, "nodes.csv"), index=False)
+    os.utime(os.path.join(d, "nodes.csv"), (t + 9, t + 9))
+    with pytest.raises(ValueError, match="node_id"):
+        fs.load_snapshot(d)
