@@ -701,13 +701,14 @@ double myc_amg_bytes_per_iteration(const myc_ctx* ctx) {
   double bytes = 0.0;
   for (int l = 0; l < S->n_levels; ++l) {
     const double nb = (double)S->lv[l].nb, rows = 3.0 * (double)S->lv[l].n;
-    const double mat = 52.0 * nb + 4.0 * rows / 3.0;          // block view + block row pointer
+    const double mat64 = 52.0 * nb + 4.0 * rows / 3.0;        // FP64 block view + block row pointer
+    const double mat = (S->f32 ? 28.0 : 52.0) * nb + 4.0 * rows / 3.0;   // what the V-cycle's sweeps stream
     const bool coarsest = l == S->n_levels - 1;
     // sweeps: matrix + gathered e (8) + r (8) + own e (8) + write (8) per row; smoothing sweeps also read dinv (16)
     const double sweeps = coarsest ? (AMG_COARSE_SWEEPS - 1) : 2;
     bytes += sweeps * (mat + 32.0 * rows) + (coarsest ? sweeps : 1.0) * 16.0 * rows;
     if (l == 0) {
-      bytes += mat + 32.0 * rows;                              // w = A u: u gathered, u own, r read, w written
+      bytes += mat64 + 32.0 * rows;                            // w = A u: u gathered, u own, r read, w written
       bytes += (13.0 * 8.0) * rows;                            // D0: u w p s x r mask dinv(2) read, p s x r e written
     } else {
       bytes += (8.0 + 8.0 + 16.0 + 8.0) * rows + 4.0 * rows;   // restriction: t of the members, r and e written, dinv, lists

@@ -35,6 +35,8 @@ extern "C" int myc_create(int device_ordinal, myc_ctx** out_ctx) {
     ctx->no_block3_spmv = g && g[0] == '1';
     const char* ss = getenv("MYC_ASM_FULL_SORT");
     ctx->asm_full_sort = ss && ss[0] == '1';
+    const char* sh = getenv("MYC_ASM_SHORT_SORT");
+    ctx->asm_short_sort = sh && sh[0] == '1';
     const char* d = getenv("MYC_ASM_DIRECT_FILL");
     ctx->asm_direct_fill = d && d[0] == '1';
     const char* y = getenv("MYC_NO_SYM3");

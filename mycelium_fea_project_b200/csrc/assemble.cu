@@ -5,10 +5,14 @@
 // exist for any node with an incident active element, so the CSR *structure* is fixed by
 // the directed node pairs (n1->n2, n2->n1) alone.  Pipeline (all on the caller's stream):
 //
-//   symbolic  count owned directed pairs per element -> exclusive scan -> emit
-//             (key = src_local<<dst_bits | dst, value = element id; per-node degree by integer
-//             atomics) -> stable LSD radix sort (radix_sort.cu) -> per node: unique
-//             neighbours (+1 for the diagonal block) -> exclusive scan -> row_ptr.
+//   symbolic  per-node degree (integer atomics) -> exclusive scan = the node's segment of the pair stream ->
+//             every element drops its directed pairs (key = src_local<<dst_bits | dst, value = element id)
+//             into the segments of its end nodes (slot by integer atomic: arrival order is arbitrary) ->
+//             each node orders its few pairs by (destination, element id) -- a TOTAL order, so the stream is
+//             bit-reproducible and equals what a stable sort of the element-ordered pairs by (source,
+//             destination) gives, i.e. scipy's COO->CSR order -> per node: unique neighbours (+1 for the
+//             diagonal block) -> exclusive scan -> row_ptr.  No sort pass over the stream at all; a mesh
+//             with a hub node (> 64 incident pairs) takes the radix-sort route instead (radix_sort.cu).
 //   numeric   one thread per owned node walks its sorted pair segment, evaluates S_e in
 //             registers (ke.cuh -- the COO stream and K_e are never materialised), sums
 //             duplicates in element order and the diagonal in (neighbour, element) order
@@ -75,10 +79,51 @@ edge_emit_kernel(const int32_t* __restrict__ n1, const int32_t* __restrict__ n2,
   }
 }
 
-// Short sort (default; MYC_ASM_FULL_SORT=1 forces the full-key sort): the radix passes cover the source-node
+// Sort-free route (default): degrees first ...
+__global__ void __launch_bounds__(AS_THREADS)
+edge_degree_kernel(const int32_t* __restrict__ n1, const int32_t* __restrict__ n2,
+                   const uint8_t* __restrict__ active, int64_t n_elem, int64_t n_nodes, int64_t nb,
+                   int64_t ne, int32_t* __restrict__ deg, int* __restrict__ bad_flag) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    if (active && !active[e]) continue;
+    const int32_t a = n1[e], b = n2[e];
+    if (a < 0 || b < 0 || a >= n_nodes || b >= n_nodes) { *bad_flag = 1; continue; }
+    if (owned(a, nb, ne)) atomicAdd(&deg[a - nb], 1);
+    if (b != a && owned(b, nb, ne)) atomicAdd(&deg[b - nb], 1);
+  }
+}
+
+// ... then every directed pair takes the next free slot of its source node's segment.  Which slot is a race;
+// segment_order_kernel removes every trace of it.
+__global__ void __launch_bounds__(AS_THREADS)
+edge_place_kernel(const int32_t* __restrict__ n1, const int32_t* __restrict__ n2,
+                  const uint8_t* __restrict__ active, int64_t n_elem, int64_t n_nodes, int64_t nb, int64_t ne,
+                  int dst_bits, const int32_t* __restrict__ edge_start, int32_t* __restrict__ fill,
+                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    if (active && !active[e]) continue;
+    const int32_t a = n1[e], b = n2[e];
+    if (a < 0 || b < 0 || a >= n_nodes || b >= n_nodes) continue;
+    if (owned(a, nb, ne)) {
+      const int32_t o = edge_start[a - nb] + atomicAdd(&fill[a - nb], 1);
+      keys[o] = ((uint64_t)(a - nb) << dst_bits) | (uint64_t)b;
+      vals[o] = (uint32_t)e;
+    }
+    if (b != a && owned(b, nb, ne)) {
+      const int32_t o = edge_start[b - nb] + atomicAdd(&fill[b - nb], 1);
+      keys[o] = ((uint64_t)(b - nb) << dst_bits) | (uint64_t)a;
+      vals[o] = (uint32_t)e;
+    }
+  }
+}
+
+// Short sort (MYC_ASM_SHORT_SORT=1; MYC_ASM_FULL_SORT=1 forces the full-key sort): the radix passes cover the source-node
 // bits only, so a node's segment arrives in emission (= element) order; this kernel orders it by destination
-// node with a stable insertion sort -- the same permutation the full-key sort produces, at O(degree^2) per
-// node (degree <= ~6 on hyphal networks).  A hub of degree d would cost d^2/2 moves in one thread, so a node
+// node (ties: element id) with an insertion sort -- the same permutation the full-key sort produces, at
+// O(degree^2) per node (degree <= ~6 on hyphal networks); the sort-free route uses it on segments that arrive
+// in arbitrary order.  A hub of degree d would cost d^2/2 moves in one thread, so a node
 // with more than AS_SHORT_SORT_MAX_DEG incident pairs raises *too_long and the host redoes the full sort.
 // Measured at 2048^2 (profiles/r2_ab_gpu1.md): assembly 1.93 -> 1.46 ms, CSR bit-identical.
 constexpr int AS_SHORT_SORT_MAX_DEG = 64;
@@ -95,7 +140,8 @@ segment_order_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, c
       const uint32_t vv = vals[k];
       const uint64_t d = kk & dmask;
       int32_t j = k - 1;
-      while (j >= es && (keys[j] & dmask) > d) {       // strictly greater: equal destinations keep element order
+      // (destination, element id): equal destinations end up in element order whatever the order of arrival
+      while (j >= es && ((keys[j] & dmask) > d || ((keys[j] & dmask) == d && vals[j] > vv))) {
         keys[j + 1] = keys[j];
         vals[j + 1] = vals[j];
         --j;
@@ -290,56 +336,81 @@ extern "C" int myc_assemble_symbolic(myc_ctx* ctx, const int32_t* d_n1, const in
   const int64_t n_local = node_end - node_begin;
   int64_t* h_pin = (int64_t*)ctx->h_pinned;
 
-  MYC_TRY(myc_ensure(ctx, ctx->edge_cnt, (size_t)(n_elem + 1) * sizeof(int32_t)));
+  const int64_t cnt_items = (n_elem > n_local ? n_elem : n_local) + 1;
+  MYC_TRY(myc_ensure(ctx, ctx->edge_cnt, (size_t)cnt_items * sizeof(int32_t)));
   MYC_TRY(myc_ensure(ctx, ctx->node_deg, (size_t)(n_local + 1) * sizeof(int32_t)));
   MYC_TRY(myc_ensure(ctx, ctx->node_bc, (size_t)(n_local + 1) * sizeof(int32_t)));
   MYC_TRY(myc_ensure(ctx, ctx->misc, 256));
-  int32_t* cnt = (int32_t*)ctx->edge_cnt.p;
+  int32_t* cnt = (int32_t*)ctx->edge_cnt.p;            // per-element pair count (sort routes) / per-node fill (place route)
   int32_t* deg = (int32_t*)ctx->node_deg.p;
   int32_t* nbc = (int32_t*)ctx->node_bc.p;
   int* bad_flag = (int*)ctx->misc.p;
+  int* too_long = bad_flag + 8;
   int64_t* d_total = (int64_t*)((char*)ctx->misc.p + 64);
-
-  MYC_CUDA(ctx, cudaMemsetAsync(bad_flag, 0, 128, st));
-  MYC_CUDA(ctx, cudaMemsetAsync(deg, 0, (size_t)(n_local + 1) * sizeof(int32_t), st));
   const int g_elem = grid_for(ctx, ceil_div64(n_elem, AS_THREADS), 8);
   const int g_node = grid_for(ctx, ceil_div64(n_local + 1, AS_THREADS), 8);
-  if (n_elem > 0) {
-    edge_count_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, n_nodes,
-                                                     node_begin, node_end, cnt, bad_flag);
-    MYC_LAUNCHED(ctx);
-  }
-  MYC_TRY(myc_exclusive_scan_i32(ctx, cnt, cnt, n_elem, false, d_total, st));
-  MYC_CUDA(ctx, cudaMemcpyAsync(h_pin, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  MYC_CUDA(ctx, cudaMemcpyAsync(h_pin + 1, bad_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-  MYC_CUDA(ctx, cudaStreamSynchronize(st));
-  const int64_t n_edges = h_pin[0];
-  if (*(int*)(h_pin + 1)) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "assemble_symbolic: element end node outside [0, n_nodes)");
-  if (n_edges >= ((int64_t)1 << 31)) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "assemble_symbolic: too many directed pairs for one device");
-
   const int dst_bits = bits_for(n_nodes);
   const int key_bits = dst_bits + bits_for(n_local);
-  for (int k = 0; k < 2; ++k) {
-    MYC_TRY(myc_ensure(ctx, ctx->sort_keys[k], (size_t)(n_edges + 1) * sizeof(uint64_t)));
-    MYC_TRY(myc_ensure(ctx, ctx->sort_vals[k], (size_t)(n_edges + 1) * sizeof(uint32_t)));
-  }
+  int64_t n_edges = 0;
   int sorted = 0;
-  int* too_long = bad_flag + 8;                       // zeroed with bad_flag above
-  // attempt 0: short sort (the whole pipeline runs speculatively; the hub flag is read with the nnz at the
-  // end, so the common case pays no extra host round trip); attempt 1: full-key sort
-  for (int attempt = ctx->asm_full_sort ? 1 : 0; attempt < 2; ++attempt) {
-    const bool short_sort = attempt == 0;
-    if (attempt == 1) MYC_CUDA(ctx, cudaMemsetAsync(deg, 0, (size_t)(n_local + 1) * sizeof(int32_t), st));
-    if (n_edges > 0) {
-      edge_emit_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, node_begin, node_end,
-                                                      dst_bits, cnt, (uint64_t*)ctx->sort_keys[0].p,
-                                                      (uint32_t*)ctx->sort_vals[0].p, deg);
-      MYC_LAUNCHED(ctx);
-      MYC_TRY(myc_radix_sort_pairs(ctx, n_edges, short_sort ? dst_bits : 0, key_bits, &sorted, st));
+  auto ensure_pairs = [&](int64_t n) -> int {
+    for (int k = 0; k < 2; ++k) {
+      MYC_TRY(myc_ensure(ctx, ctx->sort_keys[k], (size_t)(n + 1) * sizeof(uint64_t)));
+      MYC_TRY(myc_ensure(ctx, ctx->sort_vals[k], (size_t)(n + 1) * sizeof(uint32_t)));
     }
-    // per-node segments of the sorted stream
-    MYC_TRY(myc_exclusive_scan_i32(ctx, deg, deg, n_local, true, nullptr, st));
-    if (short_sort && n_edges > 0 && n_local > 0) {
+    return MYC_OK;
+  };
+  // Routes, tried in this order (a later one only if an earlier one meets a hub node; MYC_ASM_SHORT_SORT=1 /
+  // MYC_ASM_FULL_SORT=1 start further down):
+  //   0  sort-free: degrees -> segments -> atomic placement -> per-node ordering by (destination, element)
+  //   1  short sort: element-ordered emission, radix passes over the source bits, per-node ordering
+  //   2  full sort: radix passes over (source, destination)
+  // Every route runs to the end speculatively; the hub flag is read together with nnz, so the common case pays
+  // no extra host round trip.  All three produce the same pair stream, hence the same CSR, bit for bit.
+  for (int route = ctx->asm_full_sort ? 2 : ctx->asm_short_sort ? 1 : 0; route < 3; ++route) {
+    MYC_CUDA(ctx, cudaMemsetAsync(bad_flag, 0, 128, st));
+    MYC_CUDA(ctx, cudaMemsetAsync(deg, 0, (size_t)(n_local + 1) * sizeof(int32_t), st));
+    sorted = 0;
+    if (route == 0) {
+      MYC_CUDA(ctx, cudaMemsetAsync(cnt, 0, (size_t)(n_local + 1) * sizeof(int32_t), st));
+      if (n_elem > 0) {
+        edge_degree_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, n_nodes, node_begin, node_end, deg,
+                                                          bad_flag);
+        MYC_LAUNCHED(ctx);
+      }
+      MYC_TRY(myc_exclusive_scan_i32(ctx, deg, deg, n_local, true, d_total, st));
+    } else {
+      if (n_elem > 0) {
+        edge_count_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, n_nodes,
+                                                         node_begin, node_end, cnt, bad_flag);
+        MYC_LAUNCHED(ctx);
+      }
+      MYC_TRY(myc_exclusive_scan_i32(ctx, cnt, cnt, n_elem, false, d_total, st));
+    }
+    MYC_CUDA(ctx, cudaMemcpyAsync(h_pin, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaMemcpyAsync(h_pin + 1, bad_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MYC_CUDA(ctx, cudaStreamSynchronize(st));
+    n_edges = h_pin[0];
+    if (*(int*)(h_pin + 1)) MYC_FAIL(ctx, MYC_ERR_BAD_ARG, "assemble_symbolic: element end node outside [0, n_nodes)");
+    if (n_edges >= ((int64_t)1 << 31)) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "assemble_symbolic: too many directed pairs for one device");
+    MYC_TRY(ensure_pairs(n_edges));
+    if (route == 0) {
+      if (n_edges > 0) {
+        edge_place_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, n_nodes, node_begin, node_end, dst_bits,
+                                                         deg, cnt, (uint64_t*)ctx->sort_keys[0].p, (uint32_t*)ctx->sort_vals[0].p);
+        MYC_LAUNCHED(ctx);
+      }
+    } else {
+      if (n_edges > 0) {
+        edge_emit_kernel<<<g_elem, AS_THREADS, 0, st>>>(d_n1, d_n2, d_active, n_elem, node_begin, node_end,
+                                                        dst_bits, cnt, (uint64_t*)ctx->sort_keys[0].p,
+                                                        (uint32_t*)ctx->sort_vals[0].p, deg);
+        MYC_LAUNCHED(ctx);
+        MYC_TRY(myc_radix_sort_pairs(ctx, n_edges, route == 1 ? dst_bits : 0, key_bits, &sorted, st));
+      }
+      MYC_TRY(myc_exclusive_scan_i32(ctx, deg, deg, n_local, true, nullptr, st));     // per-node segments of the sorted stream
+    }
+    if (route < 2 && n_edges > 0 && n_local > 0) {
       segment_order_kernel<<<g_node, AS_THREADS, 0, st>>>((uint64_t*)ctx->sort_keys[sorted].p,
                                                           (uint32_t*)ctx->sort_vals[sorted].p, deg, n_local, dst_bits,
                                                           too_long);
@@ -356,7 +427,7 @@ extern "C" int myc_assemble_symbolic(myc_ctx* ctx, const int32_t* d_n1, const in
     MYC_CUDA(ctx, cudaMemcpyAsync(h_pin, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     MYC_CUDA(ctx, cudaMemcpyAsync(h_pin + 2, too_long, sizeof(int), cudaMemcpyDeviceToHost, st));
     MYC_CUDA(ctx, cudaStreamSynchronize(st));
-    if (!short_sort || !*(int*)(h_pin + 2)) break;    // no hub: the short sort's permutation stands
+    if (route == 2 || !*(int*)(h_pin + 2)) break;      // no hub: this route's pair stream stands
   }
   const int64_t nnz = 9 * h_pin[0];
   if (nnz >= ((int64_t)1 << 31)) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "assemble_symbolic: nnz %lld exceeds int32 row_ptr", (long long)nnz);

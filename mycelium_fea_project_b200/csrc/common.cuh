@@ -34,8 +34,9 @@ struct myc_ctx {
   bool no_block3_spmv = false;     // MYC_NO_BLOCK3_SPMV=1: ignore the node-block hint
   bool no_sym3 = false;            // MYC_NO_SYM3=1: the fused PCG streams the CSR, not the symmetric block view
   bool no_halo_overlap = true;     // MYC_HALO_OVERLAP=1 enables the gated sweep (halo waits inside the sweep)
-  bool asm_full_sort = false;      // MYC_ASM_FULL_SORT=1: radix passes over the whole (source, destination) key instead of the
-                                   // source bits + per-node neighbour ordering (the default since round 2)
+  bool asm_full_sort = false;      // MYC_ASM_FULL_SORT=1: radix passes over the whole (source, destination) key
+  bool asm_short_sort = false;     // MYC_ASM_SHORT_SORT=1: radix passes over the source bits + per-node neighbour ordering
+                                   // (default: no sort pass at all -- atomic placement into per-node segments + ordering)
   bool asm_direct_fill = false;    // MYC_ASM_DIRECT_FILL=1: numeric assembly stores rows straight to global memory (no staging)
   bool csr_block3 = false;         // caller's hint: the CSR it passes has the 3x3 node-block structure
 

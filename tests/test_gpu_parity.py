@@ -189,25 +189,33 @@ def test_assembly_staged_fill_matches_direct_fill(monkeypatch):
         ctx2.close()
 
 
-def test_assembly_short_and_full_sort_agree(monkeypatch):
-    """The default short sort (radix passes over the source bits + per-node neighbour ordering) gives the same
-    CSR, bit for bit, as the full-key sort (MYC_ASM_FULL_SORT=1); logic also checked on the CPU in
-    test_kernel_logic_host.py."""
+@pytest.mark.parametrize("route", ["MYC_ASM_SHORT_SORT", "MYC_ASM_FULL_SORT"])
+def test_assembly_routes_agree(monkeypatch, route):
+    """The default sort-free route (atomic placement into per-node segments + per-node ordering by (destination,
+    element)) gives the same CSR, bit for bit, as the radix-sort routes -- source bits + per-node ordering
+    (MYC_ASM_SHORT_SORT=1) and the full key (MYC_ASM_FULL_SORT=1) -- and is reproducible run to run although the
+    placement slots are handed out by atomics; logic also checked on the CPU in test_kernel_logic_host.py."""
     coords, n1, n2 = synth_network(128, seed=7)
     act = np.random.default_rng(7).random(len(n1)) > 0.2
-    ref = fs.assemble_global_stiffness(coords, (n1, n2), act)
-    monkeypatch.setenv("MYC_ASM_FULL_SORT", "1")
+    n1d = np.concatenate([n1, n1[:500]])                  # duplicate elements: summed in element order
+    n2d = np.concatenate([n2, n2[:500]])
+    actd = np.concatenate([act, np.ones(500, bool)])
+    ref = fs.assemble_global_stiffness(coords, (n1d, n2d), actd)
+    again = fs.assemble_global_stiffness(coords, (n1d, n2d), actd)
+    assert np.array_equal(ref.data, again.data) and np.array_equal(ref.indices, again.indices)
+    monkeypatch.setenv(route, "1")
     ctx2 = dv.Context(0)
     try:
-        K = dv.assemble(ctx2, dv.DeviceMesh.from_host(coords, n1, n2, act), fs.E_mod, fs.A, fs.I).to_scipy()
+        K = dv.assemble(ctx2, dv.DeviceMesh.from_host(coords, n1d, n2d, actd), fs.E_mod, fs.A, fs.I).to_scipy()
     finally:
         ctx2.close()
     assert np.array_equal(K.indptr, ref.indptr) and np.array_equal(K.indices, ref.indices) and np.array_equal(K.data, ref.data)
+    _assert_csr_parity(K, fo.assemble_global_stiffness(coords, n1d, n2d, actd))
 
 
 def test_assembly_hub_node_falls_back_to_full_sort(ctx):
-    """A node with more incident elements than the short sort orders in one thread (64) makes the assembler
-    redo the symbolic phase with the full-key sort: same CSR as the oracle."""
+    """A node with more incident elements than one thread orders (64) makes the assembler redo the symbolic
+    phase with the radix-sort routes (short sort, then full-key sort): same CSR as the oracle."""
     rng = np.random.default_rng(3)
     n = 200
     coords = np.c_[rng.random((n, 2)), np.zeros(n)]
