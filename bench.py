@@ -54,6 +54,7 @@ sys.path.insert(0, ROOT)
 GRIP = 1.5
 DISP = 0.02
 RTOL = 1e-10
+RTOL_ONE_SHOT = 1e-12   # the strong-scaling / configs[4] records are compared ACROSS runs (1 vs N GPUs): two more digits
 MAXIT = 400_000      # bound on PCG iterations (a mis-set problem must not burn GPU minutes)
 PUBLISHED_RAMP_S = 71.76   # /root/reference/results/sim_20251117_181147/fea_results/runtime.txt:1 (incl. plotting)
 
@@ -381,7 +382,7 @@ def run_ours(args):
         p["react_d"] = torch.from_numpy(react).to(dev)
         return p
 
-    def solve_problem(p, gather_U=False):
+    def solve_problem(p, gather_U=False, rtol=RTOL):
         """One pass of the hot path on device-resident inputs.  Returns a dict of results + timings."""
         if world > 1:
             s = p["solver"]
@@ -389,14 +390,14 @@ def run_ours(args):
             ev[0].record()
             K = s.assemble(fs.E_mod, fs.A, fs.I)
             ev[1].record()
-            r = s.load_case(K, p["kd_d"], p["kv_d"], react_dofs=p["react"], rtol=RTOL, precond=args.precond,
+            r = s.load_case(K, p["kd_d"], p["kv_d"], react_dofs=p["react"], rtol=rtol, precond=args.precond,
                             gather_U=gather_U, maxit=MAXIT)
             out = {"iterations": r["iterations"], "relres": r["relres"], "total_force": r["total_force"],
                    "ms_assemble": ev[0].elapsed_time(ev[1]), "ms_setup": r["ms_setup"], "ms_solve": r["ms_solve"],
                    "precond": r["precond"], "nnz_local": K.nnz}
             p["last"] = (K, r)
         else:
-            r = fs.analyze_load_case(p["mesh"], p["kd_d"], p["kv_d"], react_dofs=p["react_d"], rtol=RTOL,
+            r = fs.analyze_load_case(p["mesh"], p["kd_d"], p["kv_d"], react_dofs=p["react_d"], rtol=rtol,
                                      precond=args.precond)
             out = {"iterations": r.iterations, "relres": r.relres, "total_force": r.total_force,
                    "ms_assemble": r.ms_assemble, "ms_setup": r.ms_setup, "ms_solve": r.ms_solve,
@@ -554,13 +555,13 @@ def run_ours(args):
         from mycelium_fea_project_b200.synth import synth_network
         coords, n1, n2 = synth_network(*shape)
         p = make_problem(coords, n1, n2, case)
-        solve_problem(p, gather_U=parity)                       # warm (allocations, IPC mappings)
+        solve_problem(p, gather_U=parity, rtol=RTOL_ONE_SHOT)   # warm (allocations, IPC mappings)
         barrier()
         t0 = time.perf_counter()
-        r = solve_problem(p, gather_U=parity)
+        r = solve_problem(p, gather_U=parity, rtol=RTOL_ONE_SHOT)
         barrier()
         wall = time.perf_counter() - t0
-        rec = {"grid": list(shape), "n_dof": p["n_dof"], "load_case": case, "solver": f"{r['precond']}-PCG",
+        rec = {"grid": list(shape), "n_dof": p["n_dof"], "load_case": case, "solver": f"{r['precond']}-PCG", "rtol": RTOL_ONE_SHOT,
                "iterations": r["iterations"], "ms_assemble": max_over_ranks(r["ms_assemble"]),
                "ms_setup": max_over_ranks(r["ms_setup"]), "ms_solve": max_over_ranks(r["ms_solve"]),
                "ms_wall": max_over_ranks(wall * 1e3), "relres": r["relres"], "true_relres": true_relres(p),
@@ -575,7 +576,7 @@ def run_ours(args):
                     m1 = dv.DeviceMesh.from_host(coords, n1, n2)
                     K1 = dv.assemble(c1, m1, fs.E_mod, fs.A, fs.I)
                     s1 = dv.apply_dirichlet(c1, K1, p["kd_d"], p["kv_d"], precond=args.precond)
-                    x1, it1, _ = dv.pcg(c1, K1, s1, precond=args.precond, rtol=RTOL, maxit=MAXIT)
+                    x1, it1, _ = dv.pcg(c1, K1, s1, precond=args.precond, rtol=RTOL_ONE_SHOT, maxit=MAXIT)
                     U1 = dv.merge_solution(c1, K1, s1, x1)
                     F1 = dv.spmv(c1, K1, U1)
                     f1 = dv.gather_sum(c1, F1, p["react_d"])

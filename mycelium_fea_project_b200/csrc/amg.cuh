@@ -53,6 +53,7 @@ struct AmgLevelDev {                     // what the solver kernel reads (device
                                          // each) inside every rank's vector arena; own entries at 3*node_off
   int64_t give_lo[MYC_MAX_WORLD];        // DOF ranges [lo, hi) (global, this level) of MY rows that peer q gathers
   int64_t give_hi[MYC_MAX_WORLD];
+  int64_t zone_lo, zone_hi;              // own rows (local numbering) outside [zone_lo, zone_hi) may lie in a give range
   unsigned recv_mask;                    // bit q: this rank gathers rows of peer q on this level
   int32_t replicated;                    // 0: rows partitioned over the ranks (or one GPU); 1: first replicated level
                                          // (the seam: r is assembled from every rank's part); 2: replicated, deeper

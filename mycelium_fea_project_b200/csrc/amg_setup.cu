@@ -349,7 +349,7 @@ int am_peer_ensure(myc_ctx* ctx, int64_t doubles, cudaStream_t st, int* ok) {
     return MYC_OK;
   }
   ctx->amg_peer_cap = cap;
-  ctx->amg_epoch_red = ctx->amg_epoch_halo = 0;      // the flag block is new (zeroed) on every rank
+  ctx->amg_epoch_red = ctx->amg_epoch_halo = ctx->amg_epoch_seam = 0;      // the flag block is new (zeroed) on every rank
   return MYC_OK;
 }
 }  // namespace
@@ -676,7 +676,7 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
     MYC_TRY(am_peer_ensure(ctx, off + 16, st, &ok));
     if (!ok) return MYC_OK;                  // no P2P path between some pair of GPUs: collective fallback
   } else {
-    MYC_TRY(myc_ensure(ctx, S->arena, (size_t)(off + 16) * sizeof(double)));
+    MYC_TRY(myc_ensure(ctx, S->arena, (size_t)(off + 16) * sizeof(double) + 512 + myc_amg_peer_tail_bytes()));
   }
   MYC_TRY(myc_ensure(ctx, S->lv_dev, sizeof(AmgLevelDev) * AMG_MAX_LEVELS));
   MYC_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));

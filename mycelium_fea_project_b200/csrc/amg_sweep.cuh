@@ -42,17 +42,14 @@ __host__ __device__ constexpr size_t ag_smem_bytes(int warps) {
 struct AgPipe {
   unsigned char* ring;     // this warp's stage memory
   uint64_t* bars;          // [AG_MAX_STAGES]
-  uint64_t l2_stream;      // evict-first: a large level is read once per sweep, L2 is kept for the gathered vectors
-  uint64_t l2_keep;        // evict-last: the small levels of the hierarchy are re-read every iteration and fit L2
-  uint32_t phase_bits;
+  uint32_t phase_bits;     // (the L2 policies -- evict-first for the big streams, evict-last for the levels that fit L2 and
+                           // are re-read every iteration -- are created where a copy is issued: no registers held)
 };
 
 __device__ __forceinline__ void ag_pipe_init(AgPipe& pp, unsigned char* smem_base, int warps_per_block, int warp, int lane) {
   pp.ring = smem_base + (size_t)warp * ag_ring_bytes_per_warp();
   pp.bars = reinterpret_cast<uint64_t*>(smem_base + (size_t)warps_per_block * ag_ring_bytes_per_warp()) + warp * AG_MAX_STAGES;
   pp.phase_bits = 0;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pp.l2_stream));
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pp.l2_keep));
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < AG_MAX_STAGES; ++s) tm_mbar_init(&pp.bars[s], 1);
@@ -97,7 +94,9 @@ __device__ AG_SWEEP_INLINE void ag_sweep(AgPipe& pp, int64_t n_rows, const int32
     int32_t a0, a1;
     if (tm_tile_staged(lo, hi, nb4, CAPB, a0, a1)) {
       const uint32_t n = (uint32_t)(a1 - a0);
-      const uint64_t policy = keep_in_l2 ? pp.l2_keep : pp.l2_stream;
+      uint64_t policy;
+      if (keep_in_l2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+      else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       tm_mbar_expect_tx(&bars[s], n * (uint32_t)(6 * sizeof(VT) + 4));
       tm_bulk_load(s_val + (size_t)s * CAPB * 6, bval + (size_t)a0 * 6, n * (uint32_t)(6 * sizeof(VT)), &bars[s], policy);
       tm_bulk_load(s_col + (size_t)s * CAPB, bcol + a0, n * 4u, &bars[s], policy);

@@ -94,6 +94,7 @@ struct myc_ctx {
   int64_t peer_cap = 0;              // capacity of the u vector in doubles
   bool peer_ok = false;
   unsigned peer_epoch_red = 0, peer_epoch_halo = 0;
+  unsigned amg_epoch_seam = 0;
   unsigned amg_epoch_red = 0, amg_epoch_halo = 0;     // the same for the multigrid solver kernel's own flag block
   // multigrid on several GPUs (amg_setup.cu / pcg_amg.cu): one IPC-shared buffer per rank holding the gathered
   // correction vectors of all levels followed by the AgPeerSync slots/flags

@@ -326,6 +326,7 @@ extern "C" int myc_pcg_solve(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       if (dist && amg) {
         ctx->amg_epoch_red = (unsigned)fin.pAp;
         ctx->amg_epoch_halo = (unsigned)fin.rz_old;
+        ctx->amg_epoch_seam = (unsigned)fin.out[3];
       }
       if (getenv("MYC_FUSED_TIMING_PRINT"))
         fprintf(stderr, "[fused] block0 ns/iter: sweep %.0f  barrier+reduce %.0f  vector %.0f  barrier %.0f  (iters %lld)\n",

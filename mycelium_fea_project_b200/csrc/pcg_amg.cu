@@ -18,6 +18,8 @@
 // the right-hand side into every arena, and one all-rank flag exchange completes it.  Vector passes deal rows in chunks of 30 per warp (10 whole nodes), the lane of row (node, c) gets its
 // siblings' values by shuffle and applies row c of the symmetric 3x3 inverse -- the same row-per-lane layout as
 // the sweep's epilogue, so all accesses are coalesced.
+#include <stdlib.h>
+
 #include "amg.cuh"
 #include "amg_sweep.cuh"
 
@@ -34,7 +36,9 @@ static_assert(AMG_COARSE_SWEEPS >= 2 && AMG_COARSE_SWEEPS % 2 == 0, "the coarses
 struct AgPeerSync {                       // lives behind the vector arena in each rank's IPC-shared buffer
   double sums[2][MYC_MAX_WORLD][4];       // [parity][writer rank][gamma, delta, r.r, -]
   unsigned flag_red[MYC_MAX_WORLD];       // written by rank q: reductions q has published
-  unsigned flag_halo[MYC_MAX_WORLD];      // written by rank q: halo phases q has completed
+  unsigned flag_halo[MYC_MAX_WORLD];      // (unused since the flat barrier; kept for layout stability of the tail block)
+  unsigned long long arrive[MYC_MAX_WORLD];   // arrive[q]: how many BLOCKS of rank q have arrived at cross-GPU phase barriers,
+                                              // counted in THIS rank's memory by q's blocks themselves (red.release.sys)
 };
 
 struct AmgArgs {
@@ -54,8 +58,9 @@ struct AmgArgs {
   double* gsum;                           // [2][4]
   PcgScalars* sc;
   int world, rank;
-  unsigned epoch_red0, epoch_halo0;
-  unsigned recv_mask_all;                 // peers this rank gathers from on any level
+  unsigned epoch_red0, epoch_halo0;       // barrier counts carried over from earlier solves (the flags / counters are monotone)
+  unsigned epoch_seam0;
+  unsigned recv_mask_all;                 // neighbours: peers this rank exchanges halo rows with on any level (symmetric)
   unsigned long long* timing;             // -DMYC_AMG_TIMING: ns per phase slot, accumulated by block 0 ([4 l + phase], [64] = CG)
 };
 
@@ -127,7 +132,9 @@ struct AgPut {
     a->arena[a->rank][L.e_off[k] + g] = val;
     bool pushed = false;
     if constexpr (DIST) {
-      if (!L.replicated) {
+      // rows a neighbour gathers lie in [0, zone_lo) or [zone_hi, 3n) of the own rows (strips: next to the cuts);
+      // everything in between -- almost every row -- is done after the two comparisons
+      if (row < L.zone_lo || row >= L.zone_hi) {
 #pragma unroll 1
         for (int q = 0; q < a->world; ++q)
           if (g >= L.give_lo[q] && g < L.give_hi[q]) { a->arena[q][L.e_off[k] + g] = val; pushed = true; }
@@ -213,9 +220,8 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   const int NL = a.n_levels;
   double* const arena = a.arena[a.rank];
   AgPeerSync* const my_sync = a.sync[a.rank];
-  const double tol2 = a.sc->tol2;
-  unsigned epoch = 0, ep_red = a.epoch_red0, ep_halo = a.epoch_halo0;
-  bool pushed = false;                  // this thread stored into a peer since the last halo barrier
+  unsigned epoch = 0, ep_red = a.epoch_red0, ep_halo = a.epoch_halo0, ep_seam = a.epoch_seam0;
+  bool pushed = false;                  // (kept for the phases' signatures; the flat barrier releases at system scope anyway)
   const AgPut<DIST> put{&a};
   AgPipe pp;
   ag_pipe_init(pp, ag_smem, AG_WARPS, warp, lane);
@@ -268,25 +274,40 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
     }
     __syncthreads();
   };
-  // cross-GPU flag exchange inside a leader barrier: every peer is told that this rank's stores of halo phase e
-  // have been issued (all peers at every phase, so that the epochs stay in step), then the peers in `wait_mask`
-  // are awaited
-  auto flag_barrier = [&](unsigned wait_mask) {
-    ++ep_halo;
-    const unsigned e = ep_halo;
-    const bool block_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
+  // Cross-GPU phase barrier, FLAT: no leader hop.  Every block announces itself directly -- one release-add on its own
+  // GPU's counter and one on the counter each signalled peer keeps for this rank (a fire-and-forget NVLink atomic) --
+  // and then waits until its own GPU and every awaited peer have been announced by ALL their blocks.  One hop instead
+  // of arrive -> leader -> peer flags -> release (measured 10-14 us per barrier with the leader form on 2 GPUs).
+  // The release covers the whole block's stores, P2P ones included (they are ordered before it by the __syncthreads).
+  // Neighbours signal each other at every halo barrier, all ranks at the seam barrier; both sides count the same
+  // barriers, so the expected value of a counter is (barriers so far) x (blocks per GPU) -- every rank of a multi-GPU
+  // solve launches the same grid.  Counters are 64-bit and monotone across solves.
+  auto flag_barrier = [&](bool seam) {
+    if (seam) ++ep_seam; else ++ep_halo;
     pushed = false;
-    leader_barrier(block_pushed, [&](int ln) {
-      if (ln < a.world && ln != a.rank) {
-        __threadfence_system();
-        ag_st_release_sys(&a.sync[ln]->flag_halo[a.rank], e);
-        if ((wait_mask >> ln) & 1u) {
-          unsigned spins = 0;
-          while (ag_ld_acquire_sys(&my_sync->flag_halo[ln]) < e)
-            if (++spins > AG_SPIN_LIMIT) __trap();
+    __syncthreads();
+    if (threadIdx.x < (unsigned)a.world) {
+      const int q = (int)threadIdx.x;
+      const bool nbr = (a.recv_mask_all >> q) & 1u;
+      if (q == a.rank) {
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(&my_sync->arrive[a.rank]), "l"(1ull) : "memory");
+      } else if (seam || nbr) {
+        asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(&a.sync[q]->arrive[a.rank]), "l"(1ull) : "memory");
+      }
+      if (q == a.rank || seam || nbr) {
+        const unsigned long long target =
+            (unsigned long long)gridDim.x * ((q == a.rank || nbr) ? (unsigned long long)ep_halo + ep_seam : (unsigned long long)ep_seam);
+        unsigned spins = 0;
+        for (;;) {
+          unsigned long long v;
+          if (q == a.rank) asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&my_sync->arrive[q]) : "memory");
+          else asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&my_sync->arrive[q]) : "memory");
+          if (v >= target) break;
+          if (++spins > AG_SPIN_LIMIT) __trap();
         }
       }
-    });
+    }
+    __syncthreads();
   };
   // the level's gathered vector is complete everywhere it is read.  The wait covers the neighbours of ALL
   // partitioned levels (the same ranks on every level for contiguous strips), which also orders this rank's
@@ -296,7 +317,7 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
       local_barrier();
     } else {
       if (L.replicated) local_barrier();
-      else flag_barrier(a.recv_mask_all);
+      else flag_barrier(false);
     }
   };
 
@@ -425,14 +446,22 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
     }
   };
 
-  double gamma_old = 1.0, alpha_old = 1.0, rr = 0.0, alpha = 0.0, beta = 0.0;
-  long long it = 0;
-  int status = 0;   // 1 converged, 2 breakdown, 0 maxit
+  // The CG scalars are block-uniform: they live in shared memory (thread 0 updates them after each reduction), not
+  // in every thread's registers -- the kernel runs at the 64-register limit and these would be live in every phase.
+  __shared__ double s_cg[5];          // gamma_old, alpha_old, rr, alpha, beta
+  __shared__ long long s_it;
+  __shared__ int s_status;            // -1 running, 1 converged, 2 breakdown, 0 maxit
+  if (threadIdx.x == 0) {
+    s_cg[0] = 1.0; s_cg[1] = 1.0; s_cg[2] = 0.0; s_cg[3] = 0.0; s_cg[4] = 0.0;
+    s_it = 0;
+    s_status = -1;
+  }
+  __syncthreads();
   bool first = true;
   for (;;) {
     // ---- u = M^-1 r : V-cycle, its first phase fused with the CG recurrences
     tick(-1);
-    phase_d0(first, alpha, beta);
+    phase_d0(first, s_cg[3], s_cg[4]);
     first = false;
     halo_barrier(L0);
     tick(0);
@@ -449,7 +478,7 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
         if constexpr (DIST) {
           if (lv[l + 1].replicated == 1) {
             phase_restrict_seam(lv[l], lv[l + 1]);
-            flag_barrier((1u << a.world) - 1u);       // every rank's part of r has landed
+            flag_barrier(true);                       // every rank's part of r has landed
             phase_presmooth(lv[l + 1]);
             local_barrier();
             tick(4 * (l + 1));
@@ -494,6 +523,10 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
       for (int wq = 0; wq < AG_WARPS; ++wq) t += s_red[wq][threadIdx.x];
       a.partials[(size_t)blockIdx.x * 3 + threadIdx.x] = t;
     }
+#ifdef MYC_AMG_TIMING
+    local_barrier();            // timing builds only: separates the CG sweep (slot 64) from the reduction exchange (slot 65)
+    tick(64);
+#endif
     // ---- reduction barrier: every GPU obtains bit-identical global sums
     if constexpr (!DIST) {
       local_barrier();
@@ -540,29 +573,44 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
       if (threadIdx.x < 3) s_tot[threadIdx.x] = __ldcg(&a.gsum[par * 4 + threadIdx.x]);
     }
     __syncthreads();
+#ifdef MYC_AMG_TIMING
+    tick(65);
+#else
     tick(64);
-    const double gamma = s_tot[0], delta = s_tot[1];
-    rr = s_tot[2];
-    if (!isfinite(rr)) { status = 2; break; }
-    if (!(rr > tol2)) { status = 1; break; }
-    if (it >= a.maxit) { status = 0; break; }
-    beta = (it == 0) ? 0.0 : gamma / gamma_old;
-    const double denom = (it == 0) ? delta : delta - beta * gamma / alpha_old;
-    if (!(denom > 0.0) || !isfinite(gamma)) { status = 2; break; }
-    alpha = gamma / denom;
-    gamma_old = gamma;
-    alpha_old = alpha;
-    ++it;
-    __syncthreads();          // s_tot is rewritten by the next reduction
+#endif
+    if (threadIdx.x == 0) {   // every block computes the same scalars from the same bit-identical sums
+      const double gamma = s_tot[0], delta = s_tot[1], rr = s_tot[2];
+      const long long it = s_it;
+      s_cg[2] = rr;
+      int status = -1;
+      if (!isfinite(rr)) status = 2;
+      else if (!(rr > a.sc->tol2)) status = 1;
+      else if (it >= a.maxit) status = 0;
+      else {
+        const double beta = (it == 0) ? 0.0 : gamma / s_cg[0];
+        const double denom = (it == 0) ? delta : delta - beta * gamma / s_cg[1];
+        if (!(denom > 0.0) || !isfinite(gamma)) status = 2;
+        else {
+          const double alpha = gamma / denom;
+          s_cg[0] = gamma; s_cg[1] = alpha; s_cg[3] = alpha; s_cg[4] = beta;
+          s_it = it + 1;
+        }
+      }
+      s_status = status;
+    }
+    __syncthreads();          // (also: s_tot is rewritten by the next reduction)
+    if (s_status >= 0) break;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    a.sc->iters = it;
-    a.sc->rr_final = rr;
-    a.sc->red[1] = rr;
+    const int status = s_status;
+    a.sc->iters = s_it;
+    a.sc->rr_final = s_cg[2];
+    a.sc->red[1] = s_cg[2];
     a.sc->done = (status == 1);
     a.sc->breakdown = (status == 2);
     a.sc->pAp = (double)ep_red;          // final epochs, carried into the next solve by the host
     a.sc->rz_old = (double)ep_halo;
+    a.sc->out[3] = (double)ep_seam;
   }
 }
 
@@ -639,12 +687,20 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
     D.own_lo = (int32_t)H.own_lo; D.own_n = (int32_t)H.own_n;
     D.r_off = H.r_off;
     if (H.replicated == 1) D.r = (double*)ctx->amg_peer_own + H.r_off;
-    if (dist && !H.replicated)
+    D.zone_lo = 0;
+    D.zone_hi = 3 * (int64_t)H.n;                     // no row is pushed (single GPU, replicated level)
+    if (dist && !H.replicated) {
+      const int64_t own_lo = 3 * H.node_off;          // (every give range ends up inside one of the two zones by construction)
       for (int q = 0; q < ctx->world; ++q) {
         if (q == ctx->rank) continue;
         D.give_lo[q] = 3 * H.give_lo[q]; D.give_hi[q] = 3 * H.give_hi[q];
-        if (H.need_hi[q] > H.need_lo[q]) D.recv_mask |= 1u << q;
+        if (H.need_hi[q] > H.need_lo[q] || H.give_hi[q] > H.give_lo[q]) D.recv_mask |= 1u << q;   // (symmetric by construction)
+        if (D.give_hi[q] > D.give_lo[q]) {            // lower ranks read next to the low cut, higher ranks next to the high cut
+          if (q < ctx->rank) D.zone_lo = D.give_hi[q] - own_lo > D.zone_lo ? D.give_hi[q] - own_lo : D.zone_lo;
+          else D.zone_hi = D.give_lo[q] - own_lo < D.zone_hi ? D.give_lo[q] - own_lo : D.zone_hi;
+        }
       }
+    }
     recv_mask_all |= D.recv_mask;
   }
   MYC_CUDA(ctx, cudaMemcpyAsync(S->lv_dev.p, h_lv, sizeof(AmgLevelDev) * S->n_levels, cudaMemcpyHostToDevice, st));
@@ -663,9 +719,11 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
     }
     a.epoch_red0 = ctx->amg_epoch_red;
     a.epoch_halo0 = ctx->amg_epoch_halo;
+    a.epoch_seam0 = ctx->amg_epoch_seam;
     a.recv_mask_all = recv_mask_all;
   } else {
     a.arena[0] = (double*)S->arena.p;
+    a.sync[0] = (AgPeerSync*)((char*)S->arena.p + (((size_t)S->arena_doubles + 16) * sizeof(double) + 255) / 256 * 256);
   }
   a.mask0 = d_dinv;
   a.x = d_x;
@@ -687,10 +745,15 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
 #endif
   const int64_t n_tiles = ceil_div64(n_rows / 3, TmCfgSym::NODES);
   int grid = ctx->sm_count;
-  if (ceil_div64(n_tiles, AG_WARPS) < grid) grid = (int)ceil_div64(n_tiles, AG_WARPS);
+  // (several GPUs: every rank launches the full grid -- the flat cross-GPU barrier counts blocks)
+  if (!dist && ceil_div64(n_tiles, AG_WARPS) < grid) grid = (int)ceil_div64(n_tiles, AG_WARPS);
   if (grid < 1) grid = 1;
   void* params[] = {&a};
-  const void* fn = dist ? (f32 ? (const void*)pcg_amg_kernel<true, true> : (const void*)pcg_amg_kernel<true, false>)
+  // diagnostic: MYC_AMG_FORCE_DIST_KERNEL=1 runs the multi-GPU instantiation on one GPU (no peers: its flag barriers
+  // degenerate to leader barriers), which separates code-generation effects from communication when profiling
+  static const bool force_dist = getenv("MYC_AMG_FORCE_DIST_KERNEL") && getenv("MYC_AMG_FORCE_DIST_KERNEL")[0] == '1';
+  if (force_dist && !dist) MYC_CUDA(ctx, cudaMemsetAsync(a.sync[0], 0, sizeof(AgPeerSync), st));
+  const void* fn = (dist || force_dist) ? (f32 ? (const void*)pcg_amg_kernel<true, true> : (const void*)pcg_amg_kernel<true, false>)
                         : (f32 ? (const void*)pcg_amg_kernel<false, true> : (const void*)pcg_amg_kernel<false, false>);
   MYC_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(AG_THREADS), params, smem, st));
   ctx->launches++;
@@ -704,7 +767,7 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
     for (int l = 0; l < S->n_levels; ++l)
       fprintf(stderr, "  L%-2d n=%-9lld %10.1f %10.1f %10.1f %10.1f\n", l, (long long)S->lv[l].n, h[4 * l] / 1e3, h[4 * l + 1] / 1e3,
               h[4 * l + 2] / 1e3, h[4 * l + 3] / 1e3);
-    fprintf(stderr, "  CG sweep + reduction %10.1f\n", h[64] / 1e3);
+    fprintf(stderr, "  CG sweep %10.1f   reduction %10.1f\n", h[64] / 1e3, h[65] / 1e3);
   }
 #endif
   return MYC_OK;
