@@ -18,11 +18,15 @@
 
 #include "spmv_sym3.cuh"
 
+#ifndef AG_TILE_NODES
+#define AG_TILE_NODES 10
+#endif
 struct AgTile {
-  static constexpr int NODES = TmCfgSym::NODES;   // 10
-  static constexpr int ROWS = TmCfgSym::ROWS;     // 30
-  static constexpr int CAPB = TmCfgSym::CAPB;     // 56 blocks per stage
+  static constexpr int NODES = AG_TILE_NODES;                      // nodes per warp tile (<= 10: one lane per row)
+  static constexpr int ROWS = 3 * NODES;
+  static constexpr int CAPB = (NODES * 5 + 3 + 3) / 4 * 4;         // blocks per stage: 5 per node (lattice maximum) + alignment slack
 };
+static_assert(AgTile::NODES >= 4 && AgTile::NODES <= 10, "one lane per row of a tile");
 #ifndef AG_STAGES_F64
 #define AG_STAGES_F64 2
 #endif

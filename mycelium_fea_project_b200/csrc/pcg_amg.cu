@@ -743,7 +743,7 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
   a.timing = (unsigned long long*)ctx->xchg.p;
   MYC_CUDA(ctx, cudaMemsetAsync(a.timing, 0, 72 * sizeof(unsigned long long), st));
 #endif
-  const int64_t n_tiles = ceil_div64(n_rows / 3, TmCfgSym::NODES);
+  const int64_t n_tiles = ceil_div64(n_rows / 3, AgTile::NODES);
   int grid = ctx->sm_count;
   // (several GPUs: every rank launches the full grid -- the flat cross-GPU barrier counts blocks)
   if (!dist && ceil_div64(n_tiles, AG_WARPS) < grid) grid = (int)ceil_div64(n_tiles, AG_WARPS);
