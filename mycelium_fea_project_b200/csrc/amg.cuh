@@ -70,6 +70,9 @@ struct AmgLevelHost {
   int64_t agg_shift = 0;                 // what was added to this level's agg[] so that it indexes level l+1 relative
                                          // to that level's node_off (non-zero only above the seam)
   DevBuf brp, bcol, bval, dinv, agg, mptr, mlist, r, t;
+  DevBuf rep_brp, rep_bcol, rep_bval;    // seam level (replicated == 1): the all-gathered operator (brp / bcol / bval above
+                                         // then hold only this rank's rows, the input of the all-gather).  Separate,
+                                         // grow-only buffers: no cudaMalloc / cudaFree in the steady state of a load-case loop
   DevBuf bval32;                         // FP32 copy of the level's block values (level 0: of the context's sym_val)
   int64_t e_off[2] = {0, 0};
   int64_t r_off = -1;                    // seam level: r lives in the arena

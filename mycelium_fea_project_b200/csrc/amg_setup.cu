@@ -365,7 +365,7 @@ int myc_amg_destroy(myc_ctx* ctx) {
   if (!s) return MYC_OK;
   for (AmgLevelHost& L : s->lv) {
     am_drop(L.brp); am_drop(L.bcol); am_drop(L.bval); am_drop(L.dinv); am_drop(L.agg); am_drop(L.mptr); am_drop(L.mlist);
-    am_drop(L.r); am_drop(L.t); am_drop(L.bval32);
+    am_drop(L.r); am_drop(L.t); am_drop(L.bval32); am_drop(L.rep_brp); am_drop(L.rep_bcol); am_drop(L.rep_bval);
   }
   am_drop(s->lv_dev); am_drop(s->brp0); am_drop(s->arena); am_drop(s->act0); am_drop(s->act_global); am_drop(s->agg_global);
   for (DevBuf& b : s->work) am_drop(b);
@@ -601,7 +601,9 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       for (int q = 0; q < world; ++q) cb_off[q + 1] = cb_off[q] + h_all[q];
       const int64_t nb_g = cb_off[world];
       if (nb_g >= ((int64_t)1 << 31)) MYC_FAIL(ctx, MYC_ERR_CAPACITY, "amg_setup: replicated level too large");
-      DevBuf f_brp, f_bcol, f_bval;
+      DevBuf& f_brp = C->rep_brp;
+      DevBuf& f_bcol = C->rep_bcol;
+      DevBuf& f_bval = C->rep_bval;
       MYC_TRY(myc_ensure(ctx, f_brp, (size_t)(n_c_global + 2) * sizeof(int32_t)));
       MYC_TRY(myc_ensure(ctx, f_bcol, (size_t)(nb_g + 4) * sizeof(int32_t)));
       MYC_TRY(myc_ensure(ctx, f_bval, (size_t)(nb_g + 4) * 6 * sizeof(double)));
@@ -621,9 +623,6 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       MYC_TRY(myc_dist_allgatherv(ctx, f_bcol.p, boff, st));
       for (int q = 0; q <= world; ++q) boff[q] = 48 * cb_off[q];
       MYC_TRY(myc_dist_allgatherv(ctx, f_bval.p, boff, st));
-      MYC_CUDA(ctx, cudaStreamSynchronize(st));
-      am_drop(C->brp); am_drop(C->bcol); am_drop(C->bval);
-      C->brp = f_brp; C->bcol = f_bcol; C->bval = f_bval;
       C->n = n_c_global; C->nb = nb_g; C->node_off = 0;
       C->replicated = 1; C->own_lo = cnode_off; C->own_n = n_c;
       // agg[] of the level above indexes the coarse level relative to ITS node_off, which is now 0
@@ -635,9 +634,9 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
       c_off[0] = 0; c_off[1] = n_c_global;
     }
     for (int q = 0; q <= world; ++q) lvl_off[q] = (dist && !C->replicated) ? c_off[q] : (q == 0 ? 0 : C->n);
-    brp = (const int32_t*)C->brp.p;
-    bcol = (const int32_t*)C->bcol.p;
-    bval = (const double*)C->bval.p;
+    brp = (const int32_t*)(C->replicated == 1 ? C->rep_brp.p : C->brp.p);
+    bcol = (const int32_t*)(C->replicated == 1 ? C->rep_bcol.p : C->bcol.p);
+    bval = (const double*)(C->replicated == 1 ? C->rep_bval.p : C->bval.p);
     act = nullptr;
     ++lv;
   }
@@ -647,7 +646,8 @@ extern "C" int myc_amg_setup(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global
   if (S->f32)
     for (int l = 0; l < S->n_levels; ++l) {
       AmgLevelHost& H = S->lv[l];
-      const double* src = l == 0 ? (const double*)ctx->sym_val.p : (const double*)H.bval.p;
+      const double* src = l == 0 ? (const double*)ctx->sym_val.p
+                                 : (const double*)(H.replicated == 1 ? H.rep_bval.p : H.bval.p);
       MYC_TRY(myc_ensure(ctx, H.bval32, (size_t)(H.nb + 4) * 6 * sizeof(float)));
       if (H.nb > 0) {
         am_to_f32_kernel<<<grid_for(ctx, ceil_div64(6 * H.nb, AM_THREADS), 8), AM_THREADS, 0, st>>>(6 * H.nb, src, (float*)H.bval32.p);
