@@ -332,36 +332,30 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   // D0: CG recurrences (or their initialisation) + pre-smoothing of level 0
   auto phase_d0 = [&](bool first, double alpha, double beta) {
     const double* u = own(L0, 1);
-    // Two 30-row chunks per round, every load of both issued before the first store (the arrays may alias as far as the
-    // compiler knows): twice the bytes in flight per warp.  A known row is recognised by its all-zero row of D^-1
-    // (node-complete Dirichlet sets: a prescribed node's inverse block is zero, a free node's has a positive
-    // diagonal), which saves streaming the mask vector here.
-    const int stride = n_warps * 30;
-    for (int base = gw * 30; base < n0; base += 2 * stride) {
-      const int i0 = base + lane, i1 = i0 + stride;
-      const bool ok0 = lane < 30 && i0 < n0, ok1 = lane < 30 && i1 < n0;
-      const AgDinvRow m0 = ag_dinv_row(L0.dinv, i0, ok0, lane), m1 = ag_dinv_row(L0.dinv, i1, ok1, lane);
-      double ri0 = 0.0, ri1 = 0.0;
-      if (first) {
-        if (ok0) ri0 = r0[i0];
-        if (ok1) ri1 = r0[i1];
-        if (ok0) { a.p[i0] = 0.0; a.s[i0] = 0.0; }
-        if (ok1) { a.p[i1] = 0.0; a.s[i1] = 0.0; }
-      } else {
-        double ua = 0, pa = 0, wa = 0, sa = 0, xa = 0, ra = 0, ub = 0, pb = 0, wb = 0, sb = 0, xb = 0, rb = 0;
-        if (ok0) { ua = u[i0]; pa = a.p[i0]; wa = a.w[i0]; sa = a.s[i0]; xa = a.x[i0]; ra = r0[i0]; }
-        if (ok1) { ub = u[i1]; pb = a.p[i1]; wb = a.w[i1]; sb = a.s[i1]; xb = a.x[i1]; rb = r0[i1]; }
-        const bool free0 = m0.m0 != 0.0 || m0.m1 != 0.0 || m0.m2 != 0.0, free1 = m1.m0 != 0.0 || m1.m1 != 0.0 || m1.m2 != 0.0;
-        const double pi0 = ua + beta * pa, si0 = wa + beta * sa;
-        const double pi1 = ub + beta * pb, si1 = wb + beta * sb;
-        ri0 = free0 ? ra - alpha * si0 : 0.0;
-        ri1 = free1 ? rb - alpha * si1 : 0.0;
-        if (ok0) { a.p[i0] = pi0; a.s[i0] = si0; a.x[i0] = xa + alpha * pi0; r0[i0] = ri0; }
-        if (ok1) { a.p[i1] = pi1; a.s[i1] = si1; a.x[i1] = xb + alpha * pi1; r0[i1] = ri1; }
+    for (int base = gw * 30; base < n0; base += n_warps * 30) {
+      const int i = base + lane;
+      const bool ok = lane < 30 && i < n0;
+      double ri = 0.0;
+      // every load of the row is issued before the first store (the arrays may alias as far as the compiler knows)
+      const AgDinvRow m = ag_dinv_row(L0.dinv, i, ok, lane);
+      if (ok) {
+        if (first) {
+          ri = r0[i];
+          a.p[i] = 0.0;
+          a.s[i] = 0.0;
+        } else {
+          const double ui = u[i], pi0 = a.p[i], wi = a.w[i], si0 = a.s[i], xi = a.x[i], rr0 = r0[i], mk = a.mask0[i];
+          const double pi = ui + beta * pi0;
+          const double si = wi + beta * si0;
+          ri = mk != 0.0 ? rr0 - alpha * si : 0.0;
+          a.p[i] = pi;
+          a.s[i] = si;
+          a.x[i] = xi + alpha * pi;
+          r0[i] = ri;
+        }
       }
-      const double z0 = ag_dinv_mul(m0, ri0, lane), z1 = ag_dinv_mul(m1, ri1, lane);
-      if (ok0 && put(L0, 0, i0, AMG_OMEGA * z0)) pushed = true;
-      if (ok1 && put(L0, 0, i1, AMG_OMEGA * z1)) pushed = true;
+      const double z = ag_dinv_mul(m, ri, lane);
+      if (ok && put(L0, 0, i, AMG_OMEGA * z)) pushed = true;
     }
   };
   // R_l: t = r - A e   (e = buffer 0)
