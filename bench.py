@@ -624,7 +624,7 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
+        md.shutdown(ctx)                 # unmap peers' buffers everywhere, barrier, then free: the order CUDA IPC asks for
         dist.destroy_process_group()
 
 

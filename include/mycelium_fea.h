@@ -265,7 +265,8 @@ int myc_dist_set_plan(myc_ctx* ctx, const int64_t* h_node_offsets, const int64_t
  * values are stored straight into the neighbours' buffers and dot products are exchanged through
  * peer-written slots -- no NCCL call inside the iteration loop (csrc/pcg_fused.cu).  All three
  * calls are collective; myc_dist_peer_disable makes every rank use the NCCL loop again (call it
- * on all ranks if any rank failed to open a handle). */
+ * on all ranks if any rank failed to open a handle).  Growing the buffer later: every rank first calls
+ * myc_dist_release_peers, then a rank barrier, then myc_dist_peer_alloc again (importers unmap before exporters free). */
 int myc_dist_peer_alloc(myc_ctx* ctx, int64_t n_cols_capacity, uint8_t* h_out_handle64);
 int myc_dist_peer_open(myc_ctx* ctx, const uint8_t* h_handles);
 int myc_dist_peer_disable(myc_ctx* ctx);
@@ -278,6 +279,10 @@ int myc_allreduce_sum(myc_ctx* ctx, double* h_inout, int n, void* stream);
 /* Gather the owned slices of a global-length vector so that every rank holds all of it
  * (VecScatterCreateToZero + MPI_Bcast, src/fea_petsc_parallel.cpp:374-391).  Collective. */
 int myc_allgather_owned(myc_ctx* ctx, double* d_x_global, void* stream);
+/* Orderly shutdown of a multi-GPU job, step 1 of 2 (all ranks; put a rank barrier between this call and myc_destroy):
+ * unmaps every peer's memory this context had mapped for the persistent solver kernels.  CUDA IPC requires the
+ * importers to unmap before the exporter frees. */
+int myc_dist_release_peers(myc_ctx* ctx);
 
 /* ------------------------------------------------------------------------------------------
  * End-to-end load case on HOST buffers (what a caller without torch uses; bench.py "e2e"):

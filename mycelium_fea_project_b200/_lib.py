@@ -90,6 +90,7 @@ SIGNATURES = {
     "myc_dist_peer_alloc": [_p, _i64, _p],
     "myc_dist_peer_open": [_p, _p],
     "myc_dist_peer_disable": [_p],
+    "myc_dist_release_peers": [_p],
     "myc_halo_exchange": [_p, _p, _p],
     "myc_allreduce_sum": [_p, _pf64, _int, _p],
     "myc_allgather_owned": [_p, _p, _p],

@@ -297,14 +297,23 @@ void am_drop(DevBuf& b) {
   b.cap = 0;
 }
 
-void am_close_peers(myc_ctx* ctx) {
+// CUDA IPC rule: the importing processes close their mappings BEFORE the exporting process frees the allocation.
+// So teardown is two steps with a rank barrier in between (am_peer_ensure, myc_dist_release_peers + myc_destroy).
+void am_close_imports(myc_ctx* ctx) {
   for (int q = 0; q < MYC_MAX_WORLD; ++q) {
     if (ctx->amg_peer_base[q] && ctx->amg_peer_base[q] != ctx->amg_peer_own) cudaIpcCloseMemHandle(ctx->amg_peer_base[q]);
     ctx->amg_peer_base[q] = nullptr;
   }
+  if (ctx->amg) ctx->amg->valid = false;          // a multi-GPU hierarchy without its arena cannot be solved with
+}
+void am_free_own(myc_ctx* ctx) {
   if (ctx->amg_peer_own) cudaFree(ctx->amg_peer_own);
   ctx->amg_peer_own = nullptr;
   ctx->amg_peer_cap = 0;
+}
+void am_close_peers(myc_ctx* ctx) {
+  am_close_imports(ctx);
+  am_free_own(ctx);
 }
 
 // Several GPUs: the vector arena lives in one IPC-shared allocation per rank (vectors, then the AgPeerSync block).
@@ -314,10 +323,13 @@ int am_peer_ensure(myc_ctx* ctx, int64_t doubles, cudaStream_t st, int* ok) {
   *ok = 1;
   if (ctx->amg_peer_own && ctx->amg_peer_cap >= doubles) return MYC_OK;
   MYC_CUDA(ctx, cudaDeviceSynchronize());
-  // nobody may still be storing into the old buffers: all ranks pass this exchange before any of them frees
+  // nobody may still be storing into the old buffers: all ranks pass this exchange before any of them unmaps,
+  // and every rank has unmapped its imports before any owner frees
   int64_t token = 1, all[MYC_MAX_WORLD];
   MYC_TRY(myc_dist_allgather_host_i64(ctx, &token, 1, all, st));
-  am_close_peers(ctx);
+  am_close_imports(ctx);
+  MYC_TRY(myc_dist_allgather_host_i64(ctx, &token, 1, all, st));
+  am_free_own(ctx);
   const int64_t cap = doubles + doubles / 4 + 1024;
   const size_t vec_bytes = ((size_t)cap * sizeof(double) + 255) / 256 * 256;
   const size_t bytes = vec_bytes + myc_amg_peer_tail_bytes();
@@ -358,6 +370,8 @@ void* myc_amg_peer_sync_of(const myc_ctx* ctx, int q) {
   const size_t vec_bytes = ((size_t)ctx->amg_peer_cap * sizeof(double) + 255) / 256 * 256;
   return (char*)ctx->amg_peer_base[q] + vec_bytes;
 }
+
+void myc_amg_close_imports(myc_ctx* ctx) { am_close_imports(ctx); }
 
 int myc_amg_destroy(myc_ctx* ctx) {
   am_close_peers(ctx);

@@ -144,6 +144,25 @@ extern "C" int myc_dist_peer_disable(myc_ctx* ctx) {
   return MYC_OK;
 }
 
+void myc_amg_close_imports(myc_ctx* ctx);      // amg_setup.cu
+
+// Orderly multi-process shutdown, step 1 of 2: close every mapping of a PEER's memory (both solver kernels').  The
+// caller puts a rank barrier between this call and myc_destroy / re-allocation, which free the exported buffers
+// (CUDA IPC: importers unmap before the exporter frees).  Afterwards the peer-memory solvers are unavailable until
+// the buffers are set up again.
+extern "C" int myc_dist_release_peers(myc_ctx* ctx) {
+  if (!ctx) return MYC_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int q = 0; q < MYC_MAX_WORLD; ++q) {
+    if (ctx->peer_base[q] && q != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_base[q]);
+    if (q != ctx->rank) ctx->peer_base[q] = nullptr;
+  }
+  ctx->peer_ok = false;
+  myc_amg_close_imports(ctx);
+  return MYC_OK;
+}
+
 int myc_dist_destroy(myc_ctx* ctx) {
   for (int q = 0; q < MYC_MAX_WORLD; ++q) {
     if (ctx->peer_base[q] && q != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_base[q]);

@@ -147,6 +147,25 @@ def local_mesh_slice(n1, n2, node_begin, node_end):
     return idx, lo, hi
 
 
+def shutdown(ctx=None):
+    """Orderly end of a multi-GPU job (collective; call before ``dist.destroy_process_group()``): every rank unmaps
+    its peers' solver buffers, all ranks meet, then every rank destroys its context (which frees the buffers it had
+    exported) -- the order CUDA IPC asks for."""
+    import torch
+    import torch.distributed as dist
+    from . import device as dv
+    from ._lib import lib
+    ctx = dv.Context.get() if ctx is None else ctx
+    torch.cuda.synchronize()
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+        lib.myc_dist_release_peers(ctx.h)
+        dist.barrier()
+    ctx.close()
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
 class DistributedSolver:
     """Collective driver of one load case on a row-partitioned mesh.  The constructor sees the whole mesh
     description on the host (it is what a snapshot reader hands over), but each rank uploads and keeps only its
@@ -226,6 +245,11 @@ class DistributedSolver:
             return
         cap = int(n_cols * 1.05) + 1024
         handle = np.zeros(64, dtype=np.uint8)
+        if getattr(self.ctx, "peer_cap", 0) > 0:      # growing: importers unmap before the exporters free (CUDA IPC rule)
+            torch.cuda.synchronize()
+            dist.barrier()
+            lib.myc_dist_release_peers(self.ctx.h)
+            dist.barrier()
         check(self.ctx.h, lib.myc_dist_peer_alloc(self.ctx.h, cap, handle.ctypes.data_as(C.c_void_p)))
         t = torch.from_numpy(handle).to(self.ctx.device)
         gathered = [torch.empty_like(t) for _ in range(self.world)]

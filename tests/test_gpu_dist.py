@@ -80,6 +80,7 @@ def _worker(rank, world, port, N, precond, ret, no_peer=False, shape=None, case=
                 assert [l[0] for l in extra] == [l.n for l in lv_ref], (extra, [l.n for l in lv_ref])
                 assert abs(out["iterations"] - it_ref) <= max(2, it_ref // 20), (out["iterations"], it_ref)
         ret[rank] = (out["iterations"], err, out["total_force"], bool(getattr(solver.ctx, "peer_enabled", False)), extra)
+        md.shutdown(solver.ctx)          # orderly: unmap peers' buffers, barrier, free
     finally:
         dist.destroy_process_group()
 

@@ -40,5 +40,5 @@ for rep in range(2):
         tr_own_plan = dv.true_residual(ctx, K, out["system"], out["x"])
         if rank == 0:
             print(f"rep {rep} {c}: true(last installed plan)={tr_other_plan:.3e} true(own plan)={tr_own_plan:.3e}", flush=True)
-dist.barrier()
+md.shutdown(ctx)
 dist.destroy_process_group()

@@ -39,5 +39,5 @@ for rep in range(2):
                           "iterations": out["iterations"], "ms_setup": out["ms_setup"], "ms_solve": out["ms_solve"],
                           "us_per_iteration": out["ms_solve"] * 1e3 / max(out["iterations"], 1), "total_force": out["total_force"],
                           "levels": [(l["n_global"], l["replicated"]) for l in levels]}), flush=True)
-dist.barrier()
+md.shutdown(ctx)
 dist.destroy_process_group()

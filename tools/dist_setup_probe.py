@@ -43,5 +43,5 @@ for rep in range(4):
             print(json.dumps({"rep": rep, "case": c, "assemble_ms": (t1 - t0) * 1e3, "dirichlet_only_ms": (t2 - t1) * 1e3,
                               "dirichlet_plus_amg_ms": (t3 - t2) * 1e3, "amg_setup_events_ms": setup_ms,
                               "pcg_ms": (t4 - t3) * 1e3, "iterations": it}), flush=True)
-dist.barrier()
+md.shutdown(ctx)
 dist.destroy_process_group()
