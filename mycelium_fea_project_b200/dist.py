@@ -278,11 +278,12 @@ class DistributedSolver:
         return dv.true_residual(self.ctx, K, system, x)
 
     def load_case(self, K, known_dofs, known_vals, react_dofs=None, rtol=1e-10, precond="amg",
-                  maxit=500_000, reg=1e-12, gather_U=True, system=None):
+                  maxit=500_000, reg=1e-12, gather_U=True, system=None, x0=None):
         """Returns dict(U (global, on every rank if gather_U), iterations, relres, total_force).
         ``precond``: "amg" (aggregation multigrid, built collectively; prepared as "block6" where the hierarchy is
         not applicable), "block6", "block3" or "jacobi".  ``system``: reuse the Dirichlet system (and its
-        preconditioner) of an earlier call for the same K and known DOFs -- only the prescribed values are new."""
+        preconditioner) of an earlier call for the same K and known DOFs -- only the prescribed values are new.
+        ``x0``: starting guess on this rank's rows (overwritten with the solution)."""
         import torch
         from . import device as dv
         from ._lib import lib, check
@@ -302,7 +303,7 @@ class DistributedSolver:
         if precond != "amg":
             self._ensure_peer(K.n_cols)
         ev[1].record()
-        x, iters, relres = dv.pcg(ctx, K, sysd, precond=precond, rtol=rtol, maxit=maxit)
+        x, iters, relres = dv.pcg(ctx, K, sysd, x0=x0, precond=precond, rtol=rtol, maxit=maxit)
         U = dv.merge_solution(ctx, K, sysd, x)         # own rows of a zeroed global vector
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         total_force = None

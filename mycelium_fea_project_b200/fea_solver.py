@@ -284,6 +284,75 @@ def fea_ramp(coords, n1, n2, tol=None, load_case="Y", warm_start=True, verbose=F
     return rec
 
 
+def fea_ramp_distributed(coords, n1, n2, tol=None, load_case="Y", warm_start=True, verbose=False, incremental=True):
+    """The displacement ramp on N GPUs (one process per GPU, torch.distributed initialised with the nccl backend;
+    collective).  Same loop, same shortcuts and same records as ``fea_ramp``; every rank assembles and solves its row
+    block (dist.DistributedSolver), evaluates strain / failure on its own elements -- an element cut by the partition
+    lives on both sides, which take the same decision from the same gathered U -- and the per-step records are
+    combined on every rank (the caller normally writes them on rank 0 only)."""
+    import torch.distributed as tdist
+    from . import dist as md
+    ctx = _ctx()
+    tol = GRIP_LENGTH if tol is None else tol
+    axis, comp = LOAD_CASES[load_case]
+    coords = np.asarray(coords, dtype=np.float64)
+    n_elem = len(n1)
+    solver = md.DistributedSolver((coords, n1, n2), device=ctx.device)
+    mesh = solver.mesh
+    eidx = torch.from_numpy(solver.elem_index).to(ctx.device)
+    hi, lo = grip_nodes(coords, tol, axis)
+    react = 3 * hi + comp
+    rec = {"stress": [], "active": [], "disp": [], "force_disp": [], "iterations": [], "reassembled": [],
+           "solve_seconds": []}
+    x_prev, step_prev, topology_changed = None, 0, False
+    K_prev = sys_prev = None
+    for step in range(N_STEPS):
+        f = step / (N_STEPS - 1)
+        d_hi, d_lo = +DISPLACEMENT_MAX * f, -DISPLACEMENT_MAX * f
+        if verbose and solver.rank == 0:
+            print(f"Step {step + 1}/{N_STEPS} | d_hi={d_hi:.3f}, d_lo={d_lo:.3f}")
+        known_dofs, known_vals = build_bc(hi, lo, d_hi, d_lo, comp)
+        x0 = None
+        if warm_start and x_prev is not None and step_prev > 0 and not topology_changed:
+            x0 = x_prev * (step / step_prev)                 # see fea_ramp
+        reuse = incremental and K_prev is not None and not topology_changed
+        t_solve = time.time()
+        K = K_prev if reuse else solver.assemble(E_mod, globals()["A"], globals()["I"])
+        try:
+            out = solver.load_case(K, known_dofs, known_vals, react_dofs=react, rtol=PCG_RTOL, precond=PCG_PRECOND,
+                                   maxit=PCG_MAXIT, reg=REGULARISATION, gather_U=True, system=sys_prev if reuse else None, x0=x0)
+        except MyceliumFeaError as exc:
+            if solver.rank == 0:
+                print(f"Solver failure at step {step + 1}: {exc}. Saving partial results and stopping.")
+            break
+        rec["solve_seconds"].append(time.time() - t_solve)
+        rec["reassembled"].append(not reuse)
+        K_prev, sys_prev = K, out["system"]
+        x_prev, step_prev = out["x"], step
+        rec["force_disp"].append([d_hi - d_lo, out["total_force"]])
+        n_before = int(mesh.active.sum().item())
+        stress, n_active = dv.strain_update(ctx, mesh, out["U"], E_mod, MAX_STRAIN)       # this rank's elements
+        # combine: every element lives on at least one rank, cut elements on two with identical values
+        stress_g = torch.full((n_elem,), -float("inf"), dtype=torch.float64, device=ctx.device)
+        stress_g[eidx] = stress
+        active_g = torch.zeros((n_elem,), dtype=torch.int32, device=ctx.device)
+        active_g[eidx] = mesh.active.to(torch.int32)
+        flags = torch.tensor([1 if n_active != n_before else 0, n_active], dtype=torch.int64, device=ctx.device)
+        tdist.all_reduce(stress_g, op=tdist.ReduceOp.MAX)
+        tdist.all_reduce(active_g, op=tdist.ReduceOp.MAX)
+        tdist.all_reduce(flags, op=tdist.ReduceOp.SUM)
+        topology_changed = int(flags[0].item()) > 0
+        rec["stress"].append(stress_g.cpu().numpy())
+        rec["active"].append(active_g.cpu().numpy().astype(bool))
+        rec["disp"].append(out["U"].cpu().numpy())
+        rec["iterations"].append(out["iterations"])
+        if int(flags[1].item()) == 0:
+            if verbose and solver.rank == 0:
+                print(f"Simulation stopped early at step {step + 1}.")
+            break
+    return rec
+
+
 def write_results(fea_dir, rec, n_elems, total_time=None):
     """The reference's four CSVs + runtime.txt (fea_solver.py:298-333), same columns."""
     import pandas as pd
@@ -315,7 +384,14 @@ def fea_solver(results_dir, tol=None, load_case="Y", binary_outputs=None):
     fea_dir = os.path.join(results_dir, "fea_results")
     os.makedirs(fea_dir, exist_ok=True)
     coords, n1, n2 = load_snapshot(results_dir)
-    rec = fea_ramp(coords, n1, n2, tol=tol, load_case=load_case, verbose=True)
+    import torch.distributed as tdist
+    multi = tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
+    if multi:                                     # launched with torch.distributed.run: row-partitioned over the ranks
+        rec = fea_ramp_distributed(coords, n1, n2, tol=tol, load_case=load_case, verbose=True)
+        if tdist.get_rank() != 0:
+            return rec                            # rank 0 writes the files
+    else:
+        rec = fea_ramp(coords, n1, n2, tol=tol, load_case=load_case, verbose=True)
     n_dof = 3 * len(coords)
     if binary_outputs is None:
         binary_outputs = n_dof > 2_000_000       # one CSV column per DOF is unusable beyond this
@@ -339,6 +415,19 @@ def fea_solver(results_dir, tol=None, load_case="Y", binary_outputs=None):
 
 if __name__ == "__main__":
     if len(sys.argv) < 2:
-        print("Usage: python fea_solver.py <results_dir>")
+        print("Usage: python fea_solver.py <results_dir>      (N GPUs: python -m torch.distributed.run "
+              "--nproc-per-node N -m mycelium_fea_project_b200.fea_solver <results_dir>)")
         sys.exit()
-    fea_solver(sys.argv[1], tol=GRIP_LENGTH)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:          # launched by torch.distributed.run: one rank per GPU
+        import torch.distributed as tdist
+        from . import dist as md
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        try:
+            fea_solver(sys.argv[1], tol=GRIP_LENGTH)
+            md.shutdown()
+        finally:
+            tdist.destroy_process_group()
+    else:
+        fea_solver(sys.argv[1], tol=GRIP_LENGTH)
