@@ -205,35 +205,66 @@ __device__ __forceinline__ void write_block(int32_t* col_idx, double* val, int64
 }
 
 // The three CSR rows of node i (what one thread of the numeric phase produces): walk the node's
-// sorted pair segment, evaluate S_e in registers, sum duplicate pairs in element order and the
-// diagonal block in (neighbour, element) order.  `out_col`/`out_val` + `row0` address either the
-// global arrays (row0 = 9 * block_start[i]) or a warp's staging window in shared memory.
+// sorted pair segment, evaluate S_e in registers, sum duplicate pairs and the diagonal block in
+// (neighbour, element) order.  `out_col`/`out_val` + `row0` address either the global arrays
+// (row0 = 9 * block_start[i]) or a warp's staging window in shared memory.
+//
+// S_e is evaluated from the coordinates of (this node, destination node).  The destination is in the pair's
+// key, so neither the element id nor n1 / n2 is read here, and the element's own orientation does not matter:
+// myc_bar_block(p, q) and myc_bar_block(q, p) are BITWISE equal (p - q = -(q - p) exactly, and every later
+// operation is a product of two sign-flipped factors or sign-symmetric) -- checked on the CPU in
+// tests/test_kernel_logic_host.py.  The first four destinations and their coordinates are requested together
+// (degree <= 4 covers a lattice network): two dependent load latencies per node instead of four per pair.
 __device__ __forceinline__ void fill_node(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ evals,
                                           int32_t es, int32_t ee, int32_t w, int64_t self, uint64_t dmask,
                                           const double* __restrict__ coords, const int32_t* __restrict__ n1,
                                           const int32_t* __restrict__ n2, const BarConsts& bc, int32_t* out_col,
                                           double* out_val, int64_t row0) {
-  Sym3 diag = {0, 0, 0, 0, 0, 0};
-  int b = 0, diag_pos = -1;
-  int32_t k = es;
-  while (k < ee) {
-    const int64_t dst = (int64_t)(keys[k] & dmask);
-    if (dst == self) { ++k; continue; }                // n1 == n2: contributes exact zeros
-    if (diag_pos < 0 && dst > self) diag_pos = b++;
-    Sym3 acc = {0, 0, 0, 0, 0, 0};
-    do {
-      const uint32_t e = evals[k];
-      const int64_t a = n1[e], c = n2[e];
-      double L;
-      const Sym3 s = myc_bar_block(coords[3 * a], coords[3 * a + 1], coords[3 * a + 2],
-                                   coords[3 * c], coords[3 * c + 1], coords[3 * c + 2], bc, &L);
-      acc.xx += s.xx; acc.xy += s.xy; acc.xz += s.xz; acc.yy += s.yy; acc.yz += s.yz; acc.zz += s.zz;
-      diag.xx += s.xx; diag.xy += s.xy; diag.xz += s.xz; diag.yy += s.yy; diag.yz += s.yz; diag.zz += s.zz;
-      ++k;
-    } while (k < ee && (int64_t)(keys[k] & dmask) == dst);
-    write_block(out_col, out_val, row0, w, b, dst, acc, -1.0);
-    ++b;
+  (void)evals; (void)n1; (void)n2;
+  constexpr int PRE = 4;
+  int64_t dpre[PRE];
+  double qx[PRE], qy[PRE], qz[PRE];
+#pragma unroll
+  for (int u = 0; u < PRE; ++u) dpre[u] = es + u < ee ? (int64_t)(keys[es + u] & dmask) : -1;
+  const double px = coords[3 * self], py = coords[3 * self + 1], pz = coords[3 * self + 2];
+#pragma unroll
+  for (int u = 0; u < PRE; ++u) {
+    const int64_t d = dpre[u] >= 0 ? dpre[u] : self;
+    qx[u] = coords[3 * d]; qy[u] = coords[3 * d + 1]; qz[u] = coords[3 * d + 2];
   }
+  Sym3 diag = {0, 0, 0, 0, 0, 0}, acc = {0, 0, 0, 0, 0, 0};
+  int b = 0, diag_pos = -1;
+  int64_t run_dst = -1;
+  bool open = false;
+  auto flush = [&]() {
+    if (open) {
+      write_block(out_col, out_val, row0, w, b, run_dst, acc, -1.0);
+      ++b;
+      open = false;
+    }
+  };
+  auto take = [&](int64_t dst, double x, double y, double z) {
+    if (dst == self) return;                           // n1 == n2: contributes exact zeros
+    if (!open || dst != run_dst) {
+      flush();
+      if (diag_pos < 0 && dst > self) diag_pos = b++;
+      run_dst = dst;
+      acc = Sym3{0, 0, 0, 0, 0, 0};
+      open = true;
+    }
+    double L;
+    const Sym3 s = myc_bar_block(px, py, pz, x, y, z, bc, &L);
+    acc.xx += s.xx; acc.xy += s.xy; acc.xz += s.xz; acc.yy += s.yy; acc.yz += s.yz; acc.zz += s.zz;
+    diag.xx += s.xx; diag.xy += s.xy; diag.xz += s.xz; diag.yy += s.yy; diag.yz += s.yz; diag.zz += s.zz;
+  };
+#pragma unroll
+  for (int u = 0; u < PRE; ++u)
+    if (dpre[u] >= 0) take(dpre[u], qx[u], qy[u], qz[u]);
+  for (int32_t k = es + PRE; k < ee; ++k) {
+    const int64_t dst = (int64_t)(keys[k] & dmask);
+    take(dst, coords[3 * dst], coords[3 * dst + 1], coords[3 * dst + 2]);
+  }
+  flush();
   if (diag_pos < 0) diag_pos = b;
   write_block(out_col, out_val, row0, w, diag_pos, self, diag, 1.0);
 }
