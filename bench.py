@@ -688,7 +688,7 @@ def hbm_roofline(ctx, dv, fs, peak, peak_src, N=2048):
             "algorithmic_bytes_per_launch": nbytes, "l2": "256 MiB flush write between launches",
             "assembly": {"ms": asm_ms, "algorithmic_bytes": asm_bytes, "achieved": asm_bytes / (asm_ms * 1e-3) / 1e9,
                          "unit": "GB/s", "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak,
-                         "kernel": "assembly (edge emit, radix sort, scans, fill_staged_kernel): mesh -> CSR, "
+                         "kernel": "assembly (edge_degree / scan / edge_place / segment_order / block_count / row_ptr / fill_staged kernels): mesh -> CSR, "
                                    "bytes = 9 n_elem + 24 n_nodes + 12 nnz + 4 (n_dof + 1) (the algorithmic minimum)"}}
 
 
