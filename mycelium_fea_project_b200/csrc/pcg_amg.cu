@@ -36,7 +36,6 @@ static_assert(AMG_COARSE_SWEEPS >= 2 && AMG_COARSE_SWEEPS % 2 == 0, "the coarses
 struct AgPeerSync {                       // lives behind the vector arena in each rank's IPC-shared buffer
   double sums[2][MYC_MAX_WORLD][4];       // [parity][writer rank][gamma, delta, r.r, -]
   unsigned flag_red[MYC_MAX_WORLD];       // written by rank q: reductions q has published
-  unsigned flag_halo[MYC_MAX_WORLD];      // (unused since the flat barrier; kept for layout stability of the tail block)
   unsigned long long arrive[MYC_MAX_WORLD];   // arrive[q]: how many BLOCKS of rank q have arrived at cross-GPU phase barriers,
                                               // counted in THIS rank's memory by q's blocks themselves (red.release.sys)
 };
@@ -127,20 +126,18 @@ __device__ __forceinline__ double ag_dinv_apply(const double* __restrict__ dinv,
 template <bool DIST>
 struct AgPut {
   const AmgArgs* a;
-  __device__ __forceinline__ bool operator()(const AmgLevelDev& L, int k, int64_t row, double val) const {
+  __device__ __forceinline__ void operator()(const AmgLevelDev& L, int k, int64_t row, double val) const {
     const int64_t g = 3 * (int64_t)L.node_off + row;
     a->arena[a->rank][L.e_off[k] + g] = val;
-    bool pushed = false;
     if constexpr (DIST) {
       // rows a neighbour gathers lie in [0, zone_lo) or [zone_hi, 3n) of the own rows (strips: next to the cuts);
       // everything in between -- almost every row -- is done after the two comparisons
       if (row < L.zone_lo || row >= L.zone_hi) {
 #pragma unroll 1
         for (int q = 0; q < a->world; ++q)
-          if (g >= L.give_lo[q] && g < L.give_hi[q]) { a->arena[q][L.e_off[k] + g] = val; pushed = true; }
+          if (g >= L.give_lo[q] && g < L.give_hi[q]) a->arena[q][L.e_off[k] + g] = val;
       }
     }
-    return pushed;
   }
 };
 
@@ -171,7 +168,6 @@ struct EpiAgSmooth {        // e_out = e + omega D^-1 (r - (A e + reg e))
   const double* mask;
   double reg;
   AgPut<DIST> put;
-  bool* pushed;
   struct Pre { double ri, ei, mi; AgDinvRow m; };
   __device__ __forceinline__ Pre load(int64_t i) const {      // called by the lanes that own a row (lane = i % 30 + ...)
     return Pre{r[i], e_own[i], mask ? mask[i] : 1.0, ag_dinv_row(L->dinv, i, true, (int)(i % 3))};
@@ -181,7 +177,7 @@ struct EpiAgSmooth {        // e_out = e + omega D^-1 (r - (A e + reg e))
     const double z = ag_dinv_mul(pre.m, res, lane);
     if (ok) {
       const double val = pre.ei + AMG_OMEGA * z;
-      if (push) { if (put(*L, k_out, i, val)) *pushed = true; }
+      if (push) put(*L, k_out, i, val);
       else put.a->arena[put.a->rank][L->e_off[k_out] + 3 * (int64_t)L->node_off + i] = val;
     }
   }
@@ -221,7 +217,6 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   double* const arena = a.arena[a.rank];
   AgPeerSync* const my_sync = a.sync[a.rank];
   unsigned epoch = 0, ep_red = a.epoch_red0, ep_halo = a.epoch_halo0, ep_seam = a.epoch_seam0;
-  bool pushed = false;                  // (kept for the phases' signatures; the flat barrier releases at system scope anyway)
   const AgPut<DIST> put{&a};
   AgPipe pp;
   ag_pipe_init(pp, ag_smem, AG_WARPS, warp, lane);
@@ -247,11 +242,11 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   // ---- barriers
   auto local_barrier = [&]() { ag_grid_barrier(&a.bar[0], epoch); };
   // arrive / leader / release with cross-GPU work done by warp 0 of the last-arriving block
-  auto leader_barrier = [&](bool sys_release, auto&& leader_work) {
+  auto leader_barrier = [&](auto&& leader_work) {
     __syncthreads();
     if (threadIdx.x == 0) {
       ++epoch;
-      if (sys_release) __threadfence_system(); else __threadfence();
+      __threadfence();
       const unsigned old = atomicAdd(&a.bar[0], 1u);
       s_leader = (old == epoch * gridDim.x - 1u);
     }
@@ -284,7 +279,6 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
   // solve launches the same grid.  Counters are 64-bit and monotone across solves.
   auto flag_barrier = [&](bool seam) {
     if (seam) ++ep_seam; else ++ep_halo;
-    pushed = false;
     __syncthreads();
     if (threadIdx.x < (unsigned)a.world) {
       const int q = (int)threadIdx.x;
@@ -355,7 +349,7 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
         }
       }
       const double z = ag_dinv_mul(m, ri, lane);
-      if (ok && put(L0, 0, i, AMG_OMEGA * z)) pushed = true;
+      if (ok) put(L0, 0, i, AMG_OMEGA * z);
     }
   };
   // R_l: t = r - A e   (e = buffer 0)
@@ -380,7 +374,6 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
         const int64_t g = L.r_off + 3 * (int64_t)L.own_lo + i;
 #pragma unroll 1
         for (int q = 0; q < a.world; ++q) a.arena[q][g] = sum;
-        pushed = true;
       }
     }
   };
@@ -417,13 +410,13 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
         L.r[i] = sum;
       }
       const double z = ag_dinv_mul(dm, sum, lane);
-      if (ok && put(L, 0, i, AMG_OMEGA * z)) pushed = true;
+      if (ok) put(L, 0, i, AMG_OMEGA * z);
     }
   };
   // smoothing sweep: e[k_out] = e[k_in] + omega D^-1 (r - A e[k_in])
   auto phase_smooth = [&](const AmgLevelDev& L, int k_in, int k_out, const double* mask, bool push) {
     double dummy[1] = {0.0};
-    EpiAgSmooth<DIST> epi{&L, k_out, push, L.r, own(L, k_in), mask, a.reg, put, &pushed};
+    EpiAgSmooth<DIST> epi{&L, k_out, push, L.r, own(L, k_in), mask, a.reg, put};
     ag_sweep<EpiAgSmooth<DIST>, PcVal, PcStages>(pp, 3 * (int64_t)L.n, L.brp, pc_val(L), L.bcol, arena + L.e_off[k_in], epi,
                                                  dummy, gw, n_warps, lane, L.nb, L.l2_keep != 0);
   };
@@ -441,8 +434,8 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
       const double e0 = ag0 >= 0 ? e[i0] : 0.0, e1 = ag1 >= 0 ? e[i1] : 0.0;
       const double c0 = ag0 >= 0 ? ec[3 * (int64_t)ag0 + (i0 - 3 * nd0)] : 0.0;
       const double c1 = ag1 >= 0 ? ec[3 * (int64_t)ag1 + (i1 - 3 * nd1)] : 0.0;
-      if (ag0 >= 0 && put(L, 0, i0, e0 + AMG_SCALE * c0)) pushed = true;
-      if (ag1 >= 0 && put(L, 0, i1, e1 + AMG_SCALE * c1)) pushed = true;
+      if (ag0 >= 0) put(L, 0, i0, e0 + AMG_SCALE * c0);
+      if (ag1 >= 0) put(L, 0, i1, e1 + AMG_SCALE * c1);
     }
   };
 
@@ -544,7 +537,7 @@ __global__ void __launch_bounds__(AG_THREADS, 1) pcg_amg_kernel(AmgArgs a) {
       ++ep_red;
       const unsigned er = ep_red;
       const int par = (int)(er & 1u);
-      leader_barrier(false, [&](int ln) {
+      leader_barrier([&](int ln) {
         double tot[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {

@@ -137,3 +137,22 @@ def test_full_solve_residual_and_grip_equilibrium(big):
           f"|gap|={abs(gap):.2e} bound={bound:.2e} solve={res.ms_solve:.0f} ms")
     assert abs(gap) <= bound + 1e-10 * abs(r_top)
     assert abs(r_top + r_bot) <= 0.05 * abs(r_top)          # the 1e-12 I shift carries the rest (floating clusters)
+
+
+def test_multigrid_and_block_jacobi_agree_at_full_size(big):
+    """Above 512^2 the oracle's direct solve is out of reach, so parity is by the true residual (above) and by two
+    independent solvers agreeing: the multigrid PCG (pcg_amg_kernel: V-cycle with FP32 level operators) and the
+    block-Jacobi PCG (pcg_fused_kernel) share only the assembled K and the Dirichlet elimination.  Both to rtol 1e-12:
+    same reaction force to 1e-8, same displacement field to 1e-6 (the system's conditioning times the tolerance)."""
+    ctx, coords, n1, n2, mesh, K = big
+    hi, lo = fs.grip_nodes(coords, 1.5, 1)
+    kd, kv = fs.build_bc(hi, lo, 0.02, -0.02, 1)
+    a = fs.analyze_load_case(mesh, kd, kv, react_dofs=3 * hi + 1, rtol=1e-12, precond="amg", K=K)
+    Ua, fa, ita = a.U.clone(), a.total_force, a.iterations
+    assert a.system.precond == "amg"
+    b = fs.analyze_load_case(mesh, kd, kv, react_dofs=3 * hi + 1, rtol=1e-12, precond="block6", K=K)
+    assert b.system.precond == "block6" and b.iterations > 20 * ita
+    assert abs(fa - b.total_force) <= 1e-8 * abs(b.total_force), (fa, b.total_force)
+    err = float((Ua - b.U).norm() / b.U.norm())
+    print(f"2048^2 Y: amg {ita} its, block6 {b.iterations} its, relL2(U) {err:.2e}, force {fa:.10e} / {b.total_force:.10e}")
+    assert err <= 1e-6, err
