@@ -190,8 +190,13 @@ __device__ AG_SWEEP_INLINE void ag_sweep(AgPipe& pp, int64_t n_rows, const int32
         }
         __syncwarp();
         if (row_ok) {
-          const int e = my_hi - a0;
-          for (int b = my_lo - a0; b < e; ++b) sum += sp[PSTRIDE * b + comp];     // block order
+          // block order; the first five partials (a lattice node has at most five blocks) are requested together
+          const int b0 = my_lo - a0, e = my_hi - a0;
+          const double* q = sp + PSTRIDE * b0 + comp;
+          const double s0 = b0 < e ? q[0] : 0.0, s1 = b0 + 1 < e ? q[PSTRIDE] : 0.0, s2 = b0 + 2 < e ? q[2 * PSTRIDE] : 0.0;
+          const double s3 = b0 + 3 < e ? q[3 * PSTRIDE] : 0.0, s4 = b0 + 4 < e ? q[4 * PSTRIDE] : 0.0;
+          sum = (((s0 + s1) + s2) + s3) + s4;
+          for (int b = b0 + 5; b < e; ++b) sum += sp[PSTRIDE * b + comp];
         }
         tm_fence_proxy_async();
         __syncwarp();
