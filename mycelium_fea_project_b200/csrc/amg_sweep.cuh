@@ -11,7 +11,8 @@
 //     52 B per block, and twice the stages in the same shared memory.  Products and sums stay FP64.
 //
 // Tile = AgTile::NODES consecutive nodes; lane l < 3 NODES owns row l of the tile in the epilogue.  Stage layout per
-// warp: S x (CAPB x 6 values), then S x (CAPB column indices).  After the multiply the three row partials of a
+// warp: S x (CAPB x 6 values), then S x (CAPB column indices), then S x (16 block row pointers: the tile's own window of
+// brp travels with the same bulk-copy transaction, so the consumer never waits on a global load for it).  After the multiply the three row partials of a
 // block are parked in the block's own value slot (48 B or 24 B: three doubles fit either way).
 #pragma once
 #include <type_traits>
@@ -25,6 +26,8 @@ struct AgTile {
   static constexpr int NODES = AG_TILE_NODES;                      // nodes per warp tile (<= 10: one lane per row)
   static constexpr int ROWS = 3 * NODES;
   static constexpr int CAPB = (NODES * 5 + 3 + 3) / 4 * 4;         // blocks per stage: 5 per node (lattice maximum) + alignment slack
+  static constexpr int NPW = 16;                                   // block-row-pointer window per stage: the tile's NODES + 1
+                                                                   // entries from a 16-byte-aligned start (<= 3 + 11 ints)
 };
 static_assert(AgTile::NODES >= 4 && AgTile::NODES <= 10, "one lane per row of a tile");
 #ifndef AG_STAGES_F64
@@ -35,8 +38,8 @@ static_assert(AgTile::NODES >= 4 && AgTile::NODES <= 10, "one lane per row of a 
 #endif
 constexpr int AG_MAX_STAGES = AG_STAGES_F64 > AG_STAGES_F32 ? AG_STAGES_F64 : AG_STAGES_F32;
 __host__ __device__ constexpr size_t ag_ring_bytes_per_warp() {
-  constexpr size_t f64 = (size_t)AG_STAGES_F64 * AgTile::CAPB * (6 * sizeof(double) + sizeof(int32_t));
-  constexpr size_t f32 = (size_t)AG_STAGES_F32 * AgTile::CAPB * (6 * sizeof(float) + sizeof(int32_t));
+  constexpr size_t f64 = (size_t)AG_STAGES_F64 * (AgTile::CAPB * (6 * sizeof(double) + sizeof(int32_t)) + AgTile::NPW * sizeof(int32_t));
+  constexpr size_t f32 = (size_t)AG_STAGES_F32 * (AgTile::CAPB * (6 * sizeof(float) + sizeof(int32_t)) + AgTile::NPW * sizeof(int32_t));
   return f64 > f32 ? f64 : f32;
 }
 __host__ __device__ constexpr size_t ag_smem_bytes(int warps) {
@@ -85,23 +88,23 @@ __device__ AG_SWEEP_INLINE void ag_sweep(AgPipe& pp, int64_t n_rows, const int32
   const int32_t nb4 = nb_total & ~3;
   VT* const s_val = reinterpret_cast<VT*>(pp.ring);
   int32_t* const s_col = reinterpret_cast<int32_t*>(pp.ring + (size_t)S * CAPB * 6 * sizeof(VT));
+  int32_t* const s_np = s_col + (size_t)S * CAPB;
+  constexpr int NPW = AgTile::NPW;
   uint64_t* const bars = pp.bars;
   auto tile_of = [&](int j) -> int { return gw32 + j * nw32; };
   auto node_ptr = [&](int nd) -> int32_t { return brp[nd < n_nodes ? nd : n_nodes]; };
-  // lane l < NODES holds the block range [lo_l, hi_l) of node NODES*t + l
-  auto load_np = [&](int t, int32_t& lo_l, int32_t& hi_l) {
-    const int nd = t * NODES + (lane < NODES ? lane : NODES - 1);
-    lo_l = node_ptr(nd);
-    hi_l = node_ptr(nd + 1);
-  };
-  auto issue = [&](int s, int32_t lo, int32_t hi) {
+  // every tile is one bulk-copy transaction: its window of brp (always; the arrays carry >= 256 B of slack behind
+  // their last entry, common.cuh myc_ensure) plus, if the tile fits a stage, its values and column indices
+  auto issue = [&](int s, int t, int32_t lo, int32_t hi) {
     int32_t a0, a1;
-    if (tm_tile_staged(lo, hi, nb4, CAPB, a0, a1)) {
-      const uint32_t n = (uint32_t)(a1 - a0);
-      uint64_t policy;
-      if (keep_in_l2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-      else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      tm_mbar_expect_tx(&bars[s], n * (uint32_t)(6 * sizeof(VT) + 4));
+    const bool staged = tm_tile_staged(lo, hi, nb4, CAPB, a0, a1);
+    const uint32_t n = staged ? (uint32_t)(a1 - a0) : 0u;
+    uint64_t policy;
+    if (keep_in_l2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    tm_mbar_expect_tx(&bars[s], n * (uint32_t)(6 * sizeof(VT) + 4) + (uint32_t)(NPW * sizeof(int32_t)));
+    tm_bulk_load(s_np + (size_t)s * NPW, brp + ((t * NODES) & ~3), (uint32_t)(NPW * sizeof(int32_t)), &bars[s], policy);
+    if (staged) {
       tm_bulk_load(s_val + (size_t)s * CAPB * 6, bval + (size_t)a0 * 6, n * (uint32_t)(6 * sizeof(VT)), &bars[s], policy);
       tm_bulk_load(s_col + (size_t)s * CAPB, bcol + a0, n * 4u, &bars[s], policy);
     }
@@ -117,24 +120,30 @@ __device__ AG_SWEEP_INLINE void ag_sweep(AgPipe& pp, int64_t n_rows, const int32
     if (D < t_count) { pre_lo = node_ptr(tile_of(D) * NODES); pre_hi = node_ptr(tile_of(D) * NODES + NODES); }
 #pragma unroll
     for (int d = 0; d < D; ++d)
-      if (d < t_count) issue(d, lo[d], hi[d]);
+      if (d < t_count) issue(d, tile_of(d), lo[d], hi[d]);
   }
-  int32_t cur_lo = 0, cur_hi = 0, nxt_lo = 0, nxt_hi = 0;
-  load_np(tile_of(0), cur_lo, cur_hi);
-  if (t_count > 1) load_np(tile_of(1), nxt_lo, nxt_hi);
 
   for (int j = 0; j < t_count; ++j) {
     const int s = j % S;
     const int r0 = tile_of(j) * ROWS;
     if (lane == 0 && j + D < t_count) {
-      issue((j + D) % S, pre_lo, pre_hi);             // the stage tile j - 1 has just left
+      issue((j + D) % S, tile_of(j + D), pre_lo, pre_hi);      // the stage tile j - 1 has just left
       if (j + D + 1 < t_count) {
         pre_lo = node_ptr(tile_of(j + D + 1) * NODES);
         pre_hi = node_ptr(tile_of(j + D + 1) * NODES + NODES);
       }
     }
-    int32_t nn_lo = 0, nn_hi = 0;
-    if (j + 2 < t_count) load_np(tile_of(j + 2), nn_lo, nn_hi);
+    // the tile's transaction has landed: its block row pointers are in the stage (lane l < NODES: node NODES*t + l)
+    tm_mbar_wait(&bars[s], (pp.phase_bits >> s) & 1u);
+    pp.phase_bits ^= (1u << s);
+    int32_t cur_lo, cur_hi;
+    {
+      const int t0 = tile_of(j) * NODES, w0 = t0 & ~3;
+      const int nd = t0 + (lane < NODES ? lane : NODES - 1);
+      const int32_t* np = s_np + (size_t)s * NPW - w0;
+      cur_lo = np[nd < n_nodes ? nd : n_nodes];
+      cur_hi = np[nd + 1 < n_nodes ? nd + 1 : n_nodes];
+    }
     const int32_t lo = __shfl_sync(0xffffffffu, cur_lo, 0);
     const int32_t hi = __shfl_sync(0xffffffffu, cur_hi, NODES - 1);
     const int q = lane / 3, comp = lane - 3 * q;
@@ -146,16 +155,12 @@ __device__ AG_SWEEP_INLINE void ag_sweep(AgPipe& pp, int64_t n_rows, const int32
     double sum = 0.0;
     if (hi > lo) {
       int32_t a0, a1;
-      const bool staged_tile = tm_tile_staged(lo, hi, nb4, CAPB, a0, a1);
+      tm_tile_staged(lo, hi, nb4, CAPB, a0, a1);
       if (hi - a0 <= CAPB) {
         VT* sv = s_val + (size_t)s * CAPB * 6;
         int32_t* sc = s_col + (size_t)s * CAPB;
         double* sp = reinterpret_cast<double*>(sv);          // parked partials: 3 doubles per block (F32) / 6-stride (F64)
         constexpr int PSTRIDE = F32 ? 3 : 6;
-        if (staged_tile) {
-          tm_mbar_wait(&bars[s], (pp.phase_bits >> s) & 1u);
-          pp.phase_bits ^= (1u << s);
-        }
         const int first = lo - a0, last = hi - a0, staged = a1 > a0 ? a1 - a0 : 0;
         if (staged < last) {                      // ragged end of the whole array (< 4 blocks)
           const int k = (staged > first ? staged : first) + lane;
@@ -216,7 +221,5 @@ __device__ AG_SWEEP_INLINE void ag_sweep(AgPipe& pp, int64_t n_rows, const int32
     }
     if constexpr (tm_epi_warp_uniform<Epi>::value) epi.row_warp(r0 + lane, row_ok, sum, pre, acc, lane);
     else if (row_ok) epi.row(r0 + lane, sum, pre, acc);
-    cur_lo = nxt_lo; cur_hi = nxt_hi;
-    nxt_lo = nn_lo; nxt_hi = nn_hi;
   }
 }
