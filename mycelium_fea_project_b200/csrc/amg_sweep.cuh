@@ -10,7 +10,7 @@
 //     decided by the FP64 residual recurrence -- so its level operators are stored rounded to FP32: 28 B instead of
 //     52 B per block, and twice the stages in the same shared memory.  Products and sums stay FP64.
 //
-// Tile = AgTile::NODES consecutive nodes; lane l < 3 NODES owns row l of the tile in the epilogue.  Stage layout per
+// Tile = NODES consecutive nodes (AgTileT); lane l < 3 NODES owns row l of the tile in the epilogue.  Stage layout per
 // warp: S x (CAPB x 6 values), then S x (CAPB column indices), then S x (16 block row pointers: the tile's own window of
 // brp travels with the same bulk-copy transaction, so the consumer never waits on a global load for it).  After the multiply the three row partials of a
 // block are parked in the block's own value slot (48 B or 24 B: three doubles fit either way).
@@ -20,28 +20,45 @@
 #include "spmv_sym3.cuh"
 
 #ifndef AG_TILE_NODES
-#define AG_TILE_NODES 10
+#define AG_TILE_NODES 10              // nodes per warp tile of the FP32 sweeps inside the V-cycle
 #endif
-struct AgTile {
-  static constexpr int NODES = AG_TILE_NODES;                      // nodes per warp tile (<= 10: one lane per row)
+#ifndef AG_TILE_NODES_F64
+#define AG_TILE_NODES_F64 AG_TILE_NODES   // ... of the FP64 sweeps (w = A u; the V-cycle's sweeps under MYC_AMG_FP64=1)
+#endif
+template <int N>
+struct AgTileT {
+  static constexpr int NODES = N;                                  // nodes per warp tile (<= 10: one lane per row)
   static constexpr int ROWS = 3 * NODES;
   static constexpr int CAPB = (NODES * 5 + 3 + 3) / 4 * 4;         // blocks per stage: 5 per node (lattice maximum) + alignment slack
   static constexpr int NPW = 16;                                   // block-row-pointer window per stage: the tile's NODES + 1
                                                                    // entries from a 16-byte-aligned start (<= 3 + 11 ints)
+  static_assert(N >= 4 && N <= 10, "one lane per row of a tile");
 };
-static_assert(AgTile::NODES >= 4 && AgTile::NODES <= 10, "one lane per row of a tile");
+// the tile is chosen by the value type of the staged blocks
+template <class VT> struct AgTileOf { using type = AgTileT<AG_TILE_NODES_F64>; };
+template <> struct AgTileOf<float> { using type = AgTileT<AG_TILE_NODES>; };
+// Stage counts.  Shared memory is not only the ring: what the ring leaves of the SM's 256 KB array is L1, and every
+// gather / epilogue operand in flight holds an L1 line -- with 32 warps x (a tile's gathers + epilogue operands) in
+// flight a 28 KB L1 throttles the sweeps.  Three FP32 stages instead of four bring the block under 196 KB, i.e. a
+// 60 KB L1: 162.8 -> 145.7 ms per 2048^2 solve (profiles/r2_ab_l1_carveout.md); the fourth stage bought nothing.
 #ifndef AG_STAGES_F64
 #define AG_STAGES_F64 2
 #endif
 #ifndef AG_STAGES_F32
-#define AG_STAGES_F32 4
+#define AG_STAGES_F32 3
 #endif
 constexpr int AG_MAX_STAGES = AG_STAGES_F64 > AG_STAGES_F32 ? AG_STAGES_F64 : AG_STAGES_F32;
+template <class VT, int S>
+__host__ __device__ constexpr size_t ag_ring_bytes_of() {
+  using T = typename AgTileOf<VT>::type;
+  return (size_t)S * (T::CAPB * (6 * sizeof(VT) + sizeof(int32_t)) + T::NPW * sizeof(int32_t));
+}
 __host__ __device__ constexpr size_t ag_ring_bytes_per_warp() {
-  constexpr size_t f64 = (size_t)AG_STAGES_F64 * (AgTile::CAPB * (6 * sizeof(double) + sizeof(int32_t)) + AgTile::NPW * sizeof(int32_t));
-  constexpr size_t f32 = (size_t)AG_STAGES_F32 * (AgTile::CAPB * (6 * sizeof(float) + sizeof(int32_t)) + AgTile::NPW * sizeof(int32_t));
+  constexpr size_t f64 = ag_ring_bytes_of<double, AG_STAGES_F64>();
+  constexpr size_t f32 = ag_ring_bytes_of<float, AG_STAGES_F32>();
   return f64 > f32 ? f64 : f32;
 }
+static_assert(ag_ring_bytes_per_warp() % 16 == 0, "bulk-copy destinations are 16-byte aligned");
 __host__ __device__ constexpr size_t ag_smem_bytes(int warps) {
   return warps * ag_ring_bytes_per_warp() + (size_t)warps * AG_MAX_STAGES * sizeof(uint64_t) + 128;
 }
@@ -76,7 +93,8 @@ __device__ AG_SWEEP_INLINE void ag_sweep(AgPipe& pp, int64_t n_rows, const int32
                                          const VT* __restrict__ bval, const int32_t* __restrict__ bcol, const double* x,
                                          const Epi& epi, double (&acc)[Epi::NACC == 0 ? 1 : Epi::NACC], int64_t gw,
                                          int64_t n_warps, int lane, int32_t nb_total, bool keep_in_l2) {
-  constexpr int NODES = AgTile::NODES, ROWS = AgTile::ROWS, CAPB = AgTile::CAPB, D = S - 1;
+  using Tile = typename AgTileOf<VT>::type;
+  constexpr int NODES = Tile::NODES, ROWS = Tile::ROWS, CAPB = Tile::CAPB, D = S - 1;
   constexpr bool F32 = std::is_same<VT, float>::value;
   static_assert(S >= 2 && S <= AG_MAX_STAGES, "stage count");
   // 32-bit tile arithmetic (a rank holds < 2^31 rows): the kernel runs at the 64-register limit of a 1024-thread block
@@ -89,7 +107,7 @@ __device__ AG_SWEEP_INLINE void ag_sweep(AgPipe& pp, int64_t n_rows, const int32
   VT* const s_val = reinterpret_cast<VT*>(pp.ring);
   int32_t* const s_col = reinterpret_cast<int32_t*>(pp.ring + (size_t)S * CAPB * 6 * sizeof(VT));
   int32_t* const s_np = s_col + (size_t)S * CAPB;
-  constexpr int NPW = AgTile::NPW;
+  constexpr int NPW = Tile::NPW;
   uint64_t* const bars = pp.bars;
   auto tile_of = [&](int j) -> int { return gw32 + j * nw32; };
   auto node_ptr = [&](int nd) -> int32_t { return brp[nd < n_nodes ? nd : n_nodes]; };

@@ -632,6 +632,10 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
     for (const void* fn : fns) {
       int b = 0;
       MYC_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaFuncAttributes fa;
+      MYC_CUDA(ctx, cudaFuncGetAttributes(&fa, fn));
+      MYC_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         myc_carveout_percent(smem, fa.sharedSizeBytes, 1)));
       MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, AG_THREADS, smem));
       mn = b < mn ? b : mn;
     }
@@ -737,7 +741,7 @@ int myc_pcg_amg_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64_t
   a.timing = (unsigned long long*)ctx->xchg.p;
   MYC_CUDA(ctx, cudaMemsetAsync(a.timing, 0, 72 * sizeof(unsigned long long), st));
 #endif
-  const int64_t n_tiles = ceil_div64(n_rows / 3, AgTile::NODES);
+  const int64_t n_tiles = ceil_div64(n_rows / 3, AG_TILE_NODES < AG_TILE_NODES_F64 ? AG_TILE_NODES : AG_TILE_NODES_F64);
   int grid = ctx->sm_count;
   // (several GPUs: every rank launches the full grid -- the flat cross-GPU barrier counts blocks)
   if (!dist && ceil_div64(n_tiles, AG_WARPS) < grid) grid = (int)ceil_div64(n_tiles, AG_WARPS);

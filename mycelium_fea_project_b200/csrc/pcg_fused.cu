@@ -635,6 +635,10 @@ int myc_pcg_fused_try(myc_ctx* ctx, int64_t n_rows, int64_t n_cols_global, int64
       const size_t smem = fused_smem(fused_variant_op(k));
       int b = 0;
       MYC_CUDA(ctx, cudaFuncSetAttribute(fused_variant(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaFuncAttributes fa;
+      MYC_CUDA(ctx, cudaFuncGetAttributes(&fa, fused_variant(k)));
+      MYC_CUDA(ctx, cudaFuncSetAttribute(fused_variant(k), cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         myc_carveout_percent(smem, fa.sharedSizeBytes, 1)));     // (common.cuh: the rest is L1)
       MYC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fused_variant(k), FU_THREADS, smem));
       mn = b < mn ? b : mn;
     }

@@ -51,7 +51,10 @@ static_assert(TM_B3_ROWS % 3 == 0, "node-block tiles hold whole nodes");
 constexpr int TM_WARPS = 8;
 constexpr int TM_THREADS = 32 * TM_WARPS;
 constexpr int TM_STAGES = 2;
-constexpr int TM_BLOCKS_PER_SM = 4;                 // x TM_WARPS tile pipelines per SM
+#ifndef TM_BLOCKS_PER_SM_N
+#define TM_BLOCKS_PER_SM_N 4
+#endif
+constexpr int TM_BLOCKS_PER_SM = TM_BLOCKS_PER_SM_N;   // x TM_WARPS tile pipelines per SM
 // shared memory of one block of `warps` tile pipelines whose stages hold `cap` elements: the smaller
 // it is, the more of the 256 KB SM array is left to L1 for the x gathers
 __host__ __device__ constexpr size_t tm_smem_per_warp(int cap) { return (size_t)TM_STAGES * cap * (sizeof(double) + sizeof(int32_t)); }
@@ -359,6 +362,9 @@ static inline int myc_launch_spmv_tma(myc_ctx* ctx, int64_t n_rows, const int32_
   // the opt-in is per device and costs ~1 us: set it on every launch (a process may drive several GPUs)
   MYC_CUDA(ctx, cudaFuncSetAttribute(myc_spmv_tma_kernel<Cfg, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tm_smem_bytes(TM_WARPS, Cfg::CAP)));
+  MYC_CUDA(ctx, cudaFuncSetAttribute(myc_spmv_tma_kernel<Cfg, Epi>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     myc_carveout_percent(tm_smem_bytes(TM_WARPS, Cfg::CAP), sizeof(double) * (TM_THREADS / 32) + 64,
+                                                          TM_BLOCKS_PER_SM)));
   const int64_t n_tiles = ceil_div64(n_rows, Cfg::ROWS);
   const int grid = grid_for(ctx, ceil_div64(n_tiles, TM_WARPS), TM_BLOCKS_PER_SM);
   myc_spmv_tma_kernel<Cfg, Epi><<<grid, TM_THREADS, tm_smem_bytes(TM_WARPS, Cfg::CAP), st>>>(n_rows, rp, ci, v, x, epi, partials, counter,
