@@ -353,22 +353,46 @@ def fea_ramp_distributed(coords, n1, n2, tol=None, load_case="Y", warm_start=Tru
     return rec
 
 
+def _write_wide_csv(path, header, rows, steps):
+    """One CSV line per load step: the values of ``rows[k]`` followed by the 1-based step number -- byte for byte what
+    ``pandas.DataFrame(rows, columns=header[:-1]).assign(step=steps).to_csv(path, index=False)`` writes (floats in
+    their shortest round-trip form, booleans as True / False), without building a 22,125-column DataFrame: at the
+    reference's sizes the CSV formatting, not the solve, was the ramp's wall clock (CPU test: test_host_io.py).
+    Returns False (nothing written) if the data needs pandas' special cases (no rows, non-finite values)."""
+    if len(rows) == 0:
+        return False
+    a = np.asarray(rows)
+    if a.ndim != 2 or a.shape[1] != len(header) - 1:
+        return False
+    if a.dtype == np.bool_:
+        lines = [",".join(r) for r in np.where(a, "True", "False").tolist()]
+    elif a.dtype == np.float64:
+        if not np.isfinite(a).all():
+            return False                       # pandas writes NaN as an empty field
+        lines = [",".join(map(repr, r)) for r in a.tolist()]
+    else:
+        return False
+    with open(path, "w", newline="") as f:
+        f.write(",".join(header) + "\n")
+        f.write("".join(f"{ln},{int(st)}\n" for ln, st in zip(lines, steps)))
+    return True
+
+
 def write_results(fea_dir, rec, n_elems, total_time=None):
-    """The reference's four CSVs + runtime.txt (fea_solver.py:298-333), same columns."""
+    """The reference's four CSVs + runtime.txt (fea_solver.py:298-333), same columns, same bytes."""
     import pandas as pd
     os.makedirs(fea_dir, exist_ok=True)
     cols = [f"elem_{i}" for i in range(n_elems)]
     steps = np.arange(1, len(rec["stress"]) + 1)
-    df = pd.DataFrame(rec["stress"], columns=cols)
-    df["step"] = steps
-    df.to_csv(os.path.join(fea_dir, "stress_record.csv"), index=False)
-    df = pd.DataFrame(rec["active"], columns=cols)
-    df["step"] = steps
-    df.to_csv(os.path.join(fea_dir, "active_elements.csv"), index=False)
     n_dof = len(rec["disp"][0]) if rec["disp"] else 0
-    df = pd.DataFrame(rec["disp"], columns=np.arange(n_dof))
-    df["step"] = steps
-    df.to_csv(os.path.join(fea_dir, "node_displacements.csv"), index=False)
+    for name, rows, header in (("stress_record.csv", rec["stress"], cols),
+                               ("active_elements.csv", rec["active"], cols),
+                               ("node_displacements.csv", rec["disp"], [str(i) for i in range(n_dof)])):
+        path = os.path.join(fea_dir, name)
+        if not _write_wide_csv(path, header + ["step"], rows, steps):
+            df = pd.DataFrame(rows, columns=cols if header is cols else np.arange(n_dof))
+            df["step"] = steps
+            df.to_csv(path, index=False)
     pd.DataFrame(rec["force_disp"], columns=["total_displacement", "total_force"]).to_csv(
         os.path.join(fea_dir, "force_displacement.csv"), index=False)
     if total_time is not None:

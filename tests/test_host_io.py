@@ -77,3 +77,67 @@ def test_stale_sidecar_is_ignored_and_node_ids_are_checked(tmp_path):
     os.utime(os.path.join(d, "nodes.csv"), (t + 9, t + 9))
     with pytest.raises(ValueError, match="node_id"):
         fs.load_snapshot(d)
+
+
+def _pandas_reference_writer(fea_dir, rec, n_elems):
+    """What the reference writes (src/fea_solver.py:298-316): pandas DataFrames, one column per element / DOF."""
+    import os
+    import pandas as pd
+    os.makedirs(fea_dir, exist_ok=True)
+    cols = [f"elem_{i}" for i in range(n_elems)]
+    steps = np.arange(1, len(rec["stress"]) + 1)
+    for name, rows, columns in (("stress_record.csv", rec["stress"], cols), ("active_elements.csv", rec["active"], cols),
+                                ("node_displacements.csv", rec["disp"], np.arange(len(rec["disp"][0])))):
+        df = pd.DataFrame(rows, columns=columns)
+        df["step"] = steps
+        df.to_csv(os.path.join(fea_dir, name), index=False)
+    pd.DataFrame(rec["force_disp"], columns=["total_displacement", "total_force"]).to_csv(
+        os.path.join(fea_dir, "force_displacement.csv"), index=False)
+
+
+CSVS = ("stress_record.csv", "active_elements.csv", "node_displacements.csv", "force_displacement.csv")
+
+
+def test_result_writer_is_byte_identical_to_pandas(tmp_path):
+    """fea_solver.write_results formats the wide CSVs itself (the DataFrame route was the ramp's wall clock at the
+    reference's sizes); its bytes must be pandas' bytes -- shortest round-trip floats, exponents, -0.0, subnormals,
+    True / False -- and non-finite values must take the pandas route (empty field)."""
+    import filecmp
+    from mycelium_fea_project_b200 import fea_solver as fs
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.standard_normal(3000) * 10.0 ** rng.integers(-320, 300, 3000),
+                        [0.0, -0.0, 1.0, 2.0, 1e16, 1e15, 123456789012345678.0, 1e-5, 1e-4, 5e-324,
+                         1.7976931348623157e308, -1e22, 1e21, 0.1, 1 / 3]])
+    x = x[np.isfinite(x)]
+    rec = {"stress": [x, -x, x[::-1].copy()], "active": [x > 0, x < 0, x == 0], "disp": [x[:60], x[60:120], x[120:180]],
+           "force_disp": [[0.1, 0.2], [0.3, 1e-9], [-0.0, 5e-324]]}
+    _pandas_reference_writer(str(tmp_path / "a"), rec, len(x))
+    fs.write_results(str(tmp_path / "b"), rec, len(x))
+    for f in CSVS:
+        assert filecmp.cmp(tmp_path / "a" / f, tmp_path / "b" / f, shallow=False), f
+    bad = {k: [np.array(r, copy=True) for r in v] if k != "force_disp" else v for k, v in rec.items()}
+    bad["stress"][1][5] = np.nan
+    bad["disp"][0][0] = np.inf
+    _pandas_reference_writer(str(tmp_path / "c"), bad, len(x))
+    fs.write_results(str(tmp_path / "d"), bad, len(x))
+    for f in CSVS:
+        assert filecmp.cmp(tmp_path / "c" / f, tmp_path / "d" / f, shallow=False), f
+
+
+def test_result_writer_reproduces_the_reference_csv_bytes(golden_dir, tmp_path):
+    """The ramp records of the CPU oracle on the reference's committed letter fixture, written by the PRODUCT's writer,
+    are byte-equal to the CSVs the reference committed (results/test_I/fea_results)."""
+    import filecmp
+    import os
+    import pandas as pd
+    from oracle import fea_oracle as fo
+    from mycelium_fea_project_b200 import fea_solver as fs
+    src = os.path.join(golden_dir, "ref_results", "test_I")
+    nodes = pd.read_csv(os.path.join(src, "nodes.csv"))
+    elems = pd.read_csv(os.path.join(src, "elements.csv"))
+    res = fo.fea_ramp(nodes[["x", "y", "z"]].values, elems["n1"].values, elems["n2"].values,
+                      tol=0.5, disp_max=0.06, n_steps=40)
+    rec = {"stress": res.stress, "active": res.active, "disp": res.disp, "force_disp": res.force_disp}
+    fs.write_results(str(tmp_path / "fea_results"), rec, len(elems))
+    for f in CSVS:
+        assert filecmp.cmp(tmp_path / "fea_results" / f, os.path.join(src, "fea_results", f), shallow=False), f
