@@ -170,13 +170,13 @@ __host__ __device__ __forceinline__ constexpr int myc_sympack(int R, int i, int 
   return lo * R - lo * (lo - 1) / 2 + (hi - lo);
 }
 
-// Grid for grid-stride kernels: whole waves of the SM count, never more than the work.
 // Shared-memory carve-out preference (percent) for a kernel that runs `blocks_per_sm` blocks of `dynamic_bytes` +
 // `static_bytes` shared memory on an SM: the smallest configuration of the SM's 256 KB array that holds them, so that
 // the rest is L1.  Gathers and streamed operands in flight each hold an L1 line, so a kernel with many loads in flight
 // per SM is throttled by a small L1 (multigrid solver kernel at 2048^2: 162.8 ms with 28 KB of L1, 145.7 ms with
 // 60 KB; profiles/r2_ab_l1_carveout.md).  The driver rounds a preference UP to the next configuration, hence the
 // floor; left to itself it picks the larger L1 most of the time, not always.  MYC_CARVEOUT=<percent> overrides (A/B).
+// [host-test-begin carveout]  (tests/test_kernel_logic_host.py compiles this function for the host)
 static inline int myc_carveout_percent(size_t dynamic_bytes, size_t static_bytes, int blocks_per_sm) {
   if (const char* e = getenv("MYC_CARVEOUT")) return atoi(e);
   const size_t need = (size_t)blocks_per_sm * (dynamic_bytes + static_bytes + 1024);   // + what the system reserves per block
@@ -185,7 +185,9 @@ static inline int myc_carveout_percent(size_t dynamic_bytes, size_t static_bytes
     if (need <= (size_t)kb * 1024) return kb * 100 / 228;
   return 100;
 }
+// [host-test-end carveout]
 
+// Grid for grid-stride kernels: whole waves of the SM count, never more than the work.
 static inline int grid_for(const myc_ctx* ctx, int64_t n_tiles, int blocks_per_sm) {
   int64_t full = (int64_t)ctx->sm_count * blocks_per_sm;
   if (n_tiles < 1) n_tiles = 1;
